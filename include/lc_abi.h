@@ -1,0 +1,204 @@
+/*
+ * lc_abi.h - C ABI of liblc_b200.so: brute-force 256-bit Hamming matching for loop closing on B200.
+ *
+ * This is the drop-in boundary for the one data-parallel hot path of F-Fer/SLAM-Loop-Closing.
+ * The reference has no plugin/FFI mechanism: `matcher_` is a concrete cv::Ptr<cv::BFMatcher>
+ * (reference include/loop_closing.hpp:73).  The seam is therefore the bodies of
+ *     LoopClosingSystem::matchFeatures   (include/loop_closing.hpp:40, README.md:116-117)
+ *     LoopClosingSystem::detectLoops     (include/loop_closing.hpp:48, README.md:121-126)
+ * plus the `frames_.push_back` in processFrame (include/loop_closing.hpp:34,69), which must also
+ * append the frame's descriptors to the device-resident store.  include/loop_closing_b200.hpp shows
+ * the C++ adapter a maintainer would compile against OpenCV; INTEGRATION.md shows the bindings.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no C++/torch/OpenCV types cross this boundary;
+ *   - every function returns an lc_status (0 = ok) and never throws or aborts; lc_last_error()
+ *     gives the message of the last failure on that context;
+ *   - descriptors are 32-byte rows (cv::Mat CV_8UC1, n x 32, Frame::descriptors,
+ *     include/loop_closing.hpp:16); `row_stride` is in bytes so non-continuous Mats are accepted;
+ *     the library copies them before returning, the caller keeps ownership;
+ *   - empty inputs are not errors: they produce empty results, as cv::BFMatcher does;
+ *   - there is NO CPU fallback: if no CUDA device is usable lc_create fails.
+ *   - a context is driven by one application thread at a time (the reference is single-threaded).
+ */
+#ifndef LC_ABI_H
+#define LC_ABI_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LC_ABI_VERSION 1
+#define LC_DESC_BYTES 32       /* 256-bit ORB descriptor, README.md:115 */
+#define LC_MAX_ROWS_PER_KF ((1 << 20) - 1) /* rows of one frame; index shares a u32 key with the distance */
+
+typedef struct lc_ctx lc_ctx;
+
+typedef enum lc_status {
+  LC_OK = 0,
+  LC_ERR_INVALID = 1,  /* bad argument */
+  LC_ERR_CUDA = 2,     /* CUDA runtime/driver failure (message has the CUDA error string) */
+  LC_ERR_NOMEM = 3,    /* host or device allocation failed */
+  LC_ERR_CAPACITY = 4, /* caller-provided output array too small */
+  LC_ERR_IO = 5        /* lc_db_save / lc_db_load */
+} lc_status;
+
+typedef enum lc_kernel {
+  LC_KERNEL_AUTO = 0, /* library default (the measured-fastest bit-exact integer path) */
+  LC_KERNEL_POPC = 1, /* 8 x (XOR, POPC) per pair: the naive integer-popc formulation */
+  LC_KERNEL_CSA = 2   /* carry-save adder tree: 16 LOP3 + 4 POPC per pair, same result */
+} lc_kernel;
+
+/* Parameters of the path.  Defaults (lc_default_config) follow the reference header and README;
+ * the extra knobs exist because src/loop_closing.cpp is absent and README prose is ambiguous
+ * (SURVEY.md Appendix B). */
+typedef struct lc_config {
+  uint32_t struct_size;  /* = sizeof(lc_config); set by lc_default_config */
+  int32_t device;        /* CUDA device ordinal */
+  double loop_threshold; /* ctor default 0.7 (include/loop_closing.hpp:31); README.md:108 passes 0.15 */
+  int32_t min_loop_gap;  /* 30 (include/loop_closing.hpp:31, README.md:109) */
+  int32_t min_good;      /* 50 (README.md:124) */
+  int32_t filter_floor;  /* good iff d <= max(2*min_dist, filter_floor); README-literal 0 */
+  int32_t filter_strict; /* 0: "<=" ; 1: "<" */
+  int32_t min_init;      /* <0: min_dist is the true minimum; else it starts at this value */
+  int32_t gap_strict;    /* 0: cur - id >= gap ; 1: ">" */
+  int32_t thr_inclusive; /* 0: similarity > threshold ; 1: ">=" */
+  int32_t shard_rank;    /* keyframe k is stored on the context with k % shard_world == shard_rank */
+  int32_t shard_world;   /* 1 = unsharded */
+  int32_t kernel;        /* lc_kernel */
+  int32_t reserved0;
+  int64_t slab_rows;     /* descriptor rows per device slab; 0 = default (8 Mi rows = 256 MiB) */
+} lc_config;
+
+/* One record per stored keyframe, the integer facts detectLoops needs (README.md:121-126).
+ * similarity = (double)n_good / (double)min(nq, n_kf) is formed on the host from these ints so it
+ * is bit-identical to the reference's double division.  min_dist = n_good = -1 when the keyframe
+ * was not compared (closer than min_loop_gap, or an empty side). */
+typedef struct lc_kf_result {
+  int32_t frame_id;
+  int32_t n_kf;
+  int32_t min_dist;
+  int32_t n_good;
+} lc_kf_result;
+
+/* Same members, order and layout as the reference's LoopCandidate (include/loop_closing.hpp:22-27). */
+typedef struct lc_loop_candidate {
+  int32_t current_frame_id;
+  int32_t matched_frame_id;
+  int32_t num_matches;
+  double similarity_score;
+} lc_loop_candidate;
+
+/* CUDA-event timing of the last host-buffer call on the context (milliseconds). */
+typedef struct lc_timing {
+  float h2d_ms;    /* pinned staging -> device */
+  float kernel_ms; /* all kernels of the call */
+  float d2h_ms;    /* device -> pinned results */
+  float total_ms;  /* first H2D to last D2H on the stream */
+  int32_t kernel_launches;
+  int32_t path;    /* 1 = whole-keyframe scan kernel, 2 = split kernel + finalize */
+} lc_timing;
+
+int32_t lc_abi_version(void);
+void lc_default_config(lc_config* cfg);
+
+/* Create / destroy a context on cfg->device (cfg == NULL: defaults). */
+int32_t lc_create(const lc_config* cfg, lc_ctx** out);
+void lc_destroy(lc_ctx* ctx);
+/* Message of the last failed call on ctx (ctx == NULL: last lc_create failure of this thread). */
+const char* lc_last_error(const lc_ctx* ctx);
+int32_t lc_get_config(const lc_ctx* ctx, lc_config* out);
+/* loop_threshold, min_loop_gap, min_good and the filter/gap knobs may change between calls;
+ * device and sharding may not. */
+int32_t lc_set_params(lc_ctx* ctx, const lc_config* cfg);
+
+/* ---- keyframe-descriptor store: replaces frames_[i].descriptors as the matcher's train side
+ *      (include/loop_closing.hpp:16,69).  Device-resident, append-only, ragged. ---- */
+
+/* Append one keyframe (pinned staging -> device).  With sharding every rank appends every keyframe
+ * in the same order; a rank that does not own keyframe k records only (frame_id, n) and may pass
+ * desc == NULL.  *kf_index (optional) receives the global insertion index. */
+int32_t lc_db_append(lc_ctx* ctx, int32_t frame_id, const uint8_t* desc, int32_t n, size_t row_stride,
+                     int64_t* kf_index);
+/* Bulk append of `count` keyframes with contiguous 32-byte rows each; desc[i] may be NULL for
+ * keyframes this shard does not own (or when n_rows[i] == 0). */
+int32_t lc_db_append_many(lc_ctx* ctx, int32_t count, const int32_t* frame_ids, const int32_t* n_rows,
+                          const uint8_t* const* desc);
+/* Same with device-resident source rows: d_rows holds the rows of the keyframes of this call that
+ * THIS shard owns, back to back (device-to-device copy on the context's stream). */
+int32_t lc_db_append_many_device(lc_ctx* ctx, int32_t count, const int32_t* frame_ids, const int32_t* n_rows,
+                                 const void* d_rows);
+/* Global and local (this shard) keyframe / row counts; any pointer may be NULL. */
+int32_t lc_db_size(const lc_ctx* ctx, int64_t* n_keyframes, int64_t* n_rows, int64_t* n_local_keyframes,
+                   int64_t* n_local_rows);
+int32_t lc_db_clear(lc_ctx* ctx);
+/* Copy keyframe `kf_index` (global index, must be owned) back to the host: desc_out has room for
+ * cap_rows rows; *n and *frame_id receive the stored values. */
+int32_t lc_db_read(lc_ctx* ctx, int64_t kf_index, uint8_t* desc_out, int32_t cap_rows, int32_t* n,
+                   int32_t* frame_id);
+/* Persist / restore this shard of the store (raw rows + frame ids + counts). */
+int32_t lc_db_save(lc_ctx* ctx, const char* path);
+int32_t lc_db_load(lc_ctx* ctx, const char* path);
+
+/* ---- matchFeatures (include/loop_closing.hpp:40): BFMatcher(NORM_HAMMING).match(q, t) followed by
+ *      README.md:117's "2x minimum distance" filter.  Outputs have nq entries (any may be NULL):
+ *      train_idx[i]/dist[i] = DMatch(i, train_idx[i], 0, (float)dist[i]); good[i] = survives the
+ *      filter.  *n_matches = nq, or 0 when either side is empty (then nothing else is written
+ *      except *min_dist = -1, *n_good = 0). ---- */
+int32_t lc_match_pair(lc_ctx* ctx, const uint8_t* q, int32_t nq, size_t q_stride, const uint8_t* t,
+                      int32_t nt, size_t t_stride, int32_t* train_idx, int32_t* dist, uint8_t* good,
+                      int32_t* n_matches, int32_t* min_dist, int32_t* n_good);
+/* Same, the train side being stored keyframe `kf_index` (no re-upload of the resident frame). */
+int32_t lc_match_vs_keyframe(lc_ctx* ctx, const uint8_t* q, int32_t nq, size_t q_stride, int64_t kf_index,
+                             int32_t* train_idx, int32_t* dist, uint8_t* good, int32_t* n_matches,
+                             int32_t* min_dist, int32_t* n_good);
+
+/* ---- detectLoops' data-parallel part (include/loop_closing.hpp:48): the current frame against
+ *      every stored keyframe of this shard.  results[] receives one record per LOCAL keyframe in
+ *      insertion order (local slot s is global keyframe shard_rank + s*shard_world); *n_results
+ *      their number.  best_packed (optional, nq entries) = min over compared rows of
+ *      (distance << 32 | global_row), global_row counting rows of ALL keyframes in insertion order
+ *      (= OpenCV's multi-image tie-break); UINT64_MAX if nothing was compared. ---- */
+int32_t lc_loop_check(lc_ctx* ctx, const uint8_t* q, int32_t nq, size_t q_stride, int32_t current_frame_id,
+                      lc_kf_result* results, int64_t results_cap, int64_t* n_results, uint64_t* best_packed);
+/* Throughput mode: n_frames query frames in one call.  results is [n_frames][n_local_keyframes];
+ * best_packed (optional) is the concatenation of the frames' nq[i]-entry arrays. */
+int32_t lc_loop_check_batch(lc_ctx* ctx, int32_t n_frames, const uint8_t* const* q, const int32_t* nq,
+                            const int32_t* current_frame_ids, lc_kf_result* results, int64_t results_cap,
+                            uint64_t* best_packed);
+/* Host-side decision rule of README.md:121-126 over records (from one shard or gathered from all):
+ * candidate iff similarity > loop_threshold and n_good >= min_good; ascending input order. */
+int32_t lc_select_candidates(const lc_ctx* ctx, const lc_kf_result* results, int64_t n_results, int32_t nq,
+                             int32_t current_frame_id, lc_loop_candidate* out, int64_t out_cap, int64_t* n_out);
+/* detectLoops in one call (unsharded contexts): lc_loop_check + lc_select_candidates. */
+int32_t lc_detect_loops(lc_ctx* ctx, const uint8_t* q, int32_t nq, size_t q_stride, int32_t current_frame_id,
+                        lc_loop_candidate* out, int64_t out_cap, int64_t* n_out);
+
+/* ---- device-pointer variants: everything already in HBM, asynchronous on `cuda_stream`
+ *      (a cudaStream_t; NULL = the context's own stream).  d_q: contiguous 32-byte rows, 16-byte
+ *      aligned.  Used for multi-GPU merging (NCCL min all-reduce of d_best_packed, all-gather of
+ *      d_results) and for kernel-only timing.  d_best_packed may be NULL. ---- */
+int32_t lc_loop_check_device(lc_ctx* ctx, const void* d_q, int32_t nq, int32_t current_frame_id,
+                             lc_kf_result* d_results, uint64_t* d_best_packed, void* cuda_stream);
+int32_t lc_loop_check_batch_device(lc_ctx* ctx, int32_t n_frames, const void* d_q, const int32_t* nq,
+                                   const int32_t* current_frame_ids, lc_kf_result* d_results,
+                                   uint64_t* d_best_packed, void* cuda_stream);
+/* d_summary[0] = min_dist, d_summary[1] = n_good (both -1/0 when a side is empty). */
+int32_t lc_match_pair_device(lc_ctx* ctx, const void* d_q, int32_t nq, const void* d_t, int32_t nt,
+                             int32_t* d_train_idx, int32_t* d_dist, uint8_t* d_good, int32_t* d_summary,
+                             void* cuda_stream);
+
+/* ---- introspection ---- */
+int32_t lc_get_last_timing(const lc_ctx* ctx, lc_timing* out);
+/* Number of kernels this context has launched since creation (bench.py's gpu_launches). */
+int64_t lc_launch_count(const lc_ctx* ctx);
+/* Block until everything queued on the context's own stream has finished. */
+int32_t lc_synchronize(lc_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LC_ABI_H */

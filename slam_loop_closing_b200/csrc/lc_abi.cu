@@ -1,0 +1,936 @@
+// lc_abi.cu - host side of liblc_b200.so: the device-resident keyframe-descriptor store, kernel
+// dispatch and the extern "C" boundary declared in include/lc_abi.h.
+//
+// Replaces the bodies of LoopClosingSystem::matchFeatures / detectLoops and the descriptor side of
+// frames_ (reference include/loop_closing.hpp:40,48,69).  No CPU fallback: every compute entry
+// point launches the sm_100a kernels of lc_kernels.cuh or fails with LC_ERR_CUDA.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <limits>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "lc_kernels.cuh"
+
+using namespace lc;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+};
+
+constexpr size_t kPinHalfBytes = 8u << 20;  // two pinned upload halves of 8 MiB
+constexpr int64_t kDefaultSlabRows = 8ll << 20;
+constexpr size_t kScratchBudgetBytes = 256u << 20;
+constexpr int kFusedMaxNq = kMaxThreads * 8;
+
+struct Shape {  // launch shape for nq queries
+  int rq, threads, chunks;
+};
+
+}  // namespace
+
+struct lc_ctx {
+  lc_config cfg;
+  int num_sms = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t pin_ev[2] = {nullptr, nullptr};
+  std::string err;
+
+  // ---- store
+  std::vector<void*> slabs;
+  int64_t slab_rows = kDefaultSlabRows;
+  int64_t last_slab_cap = 0, last_slab_used = 0;
+  std::vector<KfEntry> h_kf;  // local keyframes
+  std::vector<int64_t> h_kf_global;
+  DevBuf d_kf;
+  size_t d_kf_synced = 0;
+  int64_t g_kf = 0, g_rows = 0, l_rows = 0;
+  int32_t max_n_local = 0;
+
+  // ---- staging / work buffers
+  uint8_t* pin_up = nullptr;  // 2 x kPinHalfBytes
+  int pin_half = 0;
+  uint8_t* pin_down = nullptr;
+  size_t pin_down_cap = 0;
+  DevBuf d_q, d_t, d_results, d_best, d_scratch, d_frames, d_pair, d_out, d_counter;
+
+  lc_timing timing{};
+  int64_t launches = 0;
+};
+
+namespace {
+
+int fail(lc_ctx* c, int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  if (c) c->err = buf; else g_create_error = buf;
+  return code;
+}
+
+#define LC_CUDA(c, expr)                                                                        \
+  do {                                                                                          \
+    cudaError_t e_ = (expr);                                                                    \
+    if (e_ != cudaSuccess)                                                                      \
+      return fail((c), e_ == cudaErrorMemoryAllocation ? LC_ERR_NOMEM : LC_ERR_CUDA, "%s: %s", #expr, \
+                  cudaGetErrorString(e_));                                                      \
+  } while (0)
+
+#define LC_TRY(expr)          \
+  do {                        \
+    int rc_ = (expr);         \
+    if (rc_ != LC_OK) return rc_; \
+  } while (0)
+
+int ensure(lc_ctx* c, DevBuf& b, size_t bytes) {
+  if (bytes <= b.cap) return LC_OK;
+  size_t ncap = std::max(bytes, b.cap * 2);
+  ncap = (ncap + 255) & ~size_t(255);
+  // the old buffer may still be read by queued work on the context's stream
+  if (b.p) {
+    LC_CUDA(c, cudaStreamSynchronize(c->stream));
+    LC_CUDA(c, cudaFree(b.p));
+    b.p = nullptr;
+    b.cap = 0;
+  }
+  LC_CUDA(c, cudaMalloc(&b.p, ncap));
+  b.cap = ncap;
+  return LC_OK;
+}
+
+int ensure_pin_down(lc_ctx* c, size_t bytes) {
+  if (bytes <= c->pin_down_cap) return LC_OK;
+  if (c->pin_down) {
+    LC_CUDA(c, cudaStreamSynchronize(c->stream));
+    LC_CUDA(c, cudaFreeHost(c->pin_down));
+    c->pin_down = nullptr;
+    c->pin_down_cap = 0;
+  }
+  size_t ncap = std::max(bytes, c->pin_down_cap * 2);
+  LC_CUDA(c, cudaMallocHost((void**)&c->pin_down, ncap));
+  c->pin_down_cap = ncap;
+  return LC_OK;
+}
+
+Knobs knobs_of(const lc_config& g) {
+  return Knobs{g.min_loop_gap, g.gap_strict, g.filter_floor, g.filter_strict, g.min_init};
+}
+
+int mode_of(const lc_config& g) { return g.kernel == LC_KERNEL_POPC ? MODE_POPC : MODE_CSA; }
+
+int validate(lc_ctx* c, const lc_config& g) {
+  if (g.shard_world < 1 || g.shard_rank < 0 || g.shard_rank >= g.shard_world)
+    return fail(c, LC_ERR_INVALID, "shard_rank %d / shard_world %d invalid", g.shard_rank, g.shard_world);
+  if (g.kernel < LC_KERNEL_AUTO || g.kernel > LC_KERNEL_CSA) return fail(c, LC_ERR_INVALID, "unknown kernel %d", g.kernel);
+  if (g.slab_rows < 0) return fail(c, LC_ERR_INVALID, "slab_rows < 0");
+  if (g.min_loop_gap < -(1 << 30) || g.min_loop_gap > (1 << 30)) return fail(c, LC_ERR_INVALID, "min_loop_gap out of range");
+  return LC_OK;
+}
+
+// ---------------------------------------------------------------- store
+// rows for a new keyframe: contiguous, inside one slab
+int slab_alloc(lc_ctx* c, int64_t n, uint4** out) {
+  if (n == 0) {
+    *out = nullptr;
+    return LC_OK;
+  }
+  if (c->slabs.empty() || c->last_slab_used + n > c->last_slab_cap) {
+    const int64_t cap = std::max<int64_t>(c->slab_rows, n);
+    void* p = nullptr;
+    LC_CUDA(c, cudaMalloc(&p, (size_t)cap * LC_DESC_BYTES));
+    c->slabs.push_back(p);
+    c->last_slab_cap = cap;
+    c->last_slab_used = 0;
+  }
+  *out = (uint4*)((uint8_t*)c->slabs.back() + (size_t)c->last_slab_used * LC_DESC_BYTES);
+  c->last_slab_used += n;
+  return LC_OK;
+}
+
+// host rows (any stride) -> device `dst` through the two pinned halves: the CPU packs one half while
+// the copy engine drains the other
+int upload_rows(lc_ctx* c, uint8_t* dst, const uint8_t* src, int64_t n, size_t stride) {
+  const int64_t half_rows = (int64_t)(kPinHalfBytes / LC_DESC_BYTES);
+  for (int64_t done = 0; done < n;) {
+    uint8_t* half = c->pin_up + (size_t)c->pin_half * kPinHalfBytes;
+    const int64_t take = std::min(half_rows, n - done);
+    if (stride == LC_DESC_BYTES) {
+      memcpy(half, src + (size_t)done * LC_DESC_BYTES, (size_t)take * LC_DESC_BYTES);
+    } else {
+      for (int64_t r = 0; r < take; ++r)
+        memcpy(half + (size_t)r * LC_DESC_BYTES, src + (size_t)(done + r) * stride, LC_DESC_BYTES);
+    }
+    LC_CUDA(c, cudaMemcpyAsync(dst + (size_t)done * LC_DESC_BYTES, half, (size_t)take * LC_DESC_BYTES,
+                               cudaMemcpyHostToDevice, c->stream));
+    LC_CUDA(c, cudaEventRecord(c->pin_ev[c->pin_half], c->stream));
+    c->pin_half ^= 1;
+    LC_CUDA(c, cudaEventSynchronize(c->pin_ev[c->pin_half]));  // the half we fill next has drained
+    done += take;
+  }
+  return LC_OK;
+}
+
+int store_append(lc_ctx* c, int32_t frame_id, const uint8_t* desc, int32_t n, size_t stride, bool device_src,
+                 int64_t* kf_index) {
+  if (n < 0 || n > LC_MAX_ROWS_PER_KF) return fail(c, LC_ERR_INVALID, "n = %d outside [0, %d]", n, LC_MAX_ROWS_PER_KF);
+  const int64_t k = c->g_kf;
+  const bool own = (k % c->cfg.shard_world) == c->cfg.shard_rank;
+  if (own) {
+    if (n > 0 && !desc) return fail(c, LC_ERR_INVALID, "keyframe %lld is owned by this shard but desc is NULL", (long long)k);
+    if (!device_src && n > 0 && stride < LC_DESC_BYTES) return fail(c, LC_ERR_INVALID, "row_stride %zu < 32", stride);
+    uint4* rows = nullptr;
+    LC_TRY(slab_alloc(c, n, &rows));
+    if (n > 0) {
+      if (device_src)
+        LC_CUDA(c, cudaMemcpyAsync(rows, desc, (size_t)n * LC_DESC_BYTES, cudaMemcpyDeviceToDevice, c->stream));
+      else
+        LC_TRY(upload_rows(c, (uint8_t*)rows, desc, n, stride));
+    }
+    c->h_kf.push_back(KfEntry{rows, n, frame_id, c->g_rows});
+    c->h_kf_global.push_back(k);
+    c->l_rows += n;
+    c->max_n_local = std::max(c->max_n_local, n);
+  }
+  if (kf_index) *kf_index = k;
+  c->g_kf += 1;
+  c->g_rows += n;
+  return LC_OK;
+}
+
+int sync_kf_table(lc_ctx* c) {
+  const size_t n = c->h_kf.size();
+  if (n == c->d_kf_synced) return LC_OK;
+  if (n * sizeof(KfEntry) > c->d_kf.cap) {
+    LC_TRY(ensure(c, c->d_kf, std::max<size_t>(n * 2, 1024) * sizeof(KfEntry)));
+    c->d_kf_synced = 0;
+  }
+  LC_CUDA(c, cudaMemcpyAsync((KfEntry*)c->d_kf.p + c->d_kf_synced, c->h_kf.data() + c->d_kf_synced,
+                             (n - c->d_kf_synced) * sizeof(KfEntry), cudaMemcpyHostToDevice, c->stream));
+  // h_kf may reallocate on the next append: the copy above must have left the host vector
+  LC_CUDA(c, cudaStreamSynchronize(c->stream));
+  c->d_kf_synced = n;
+  return LC_OK;
+}
+
+// ---------------------------------------------------------------- dispatch
+Shape scan_shape(int nq) {  // whole-keyframe kernel: one chunk must hold all queries
+  Shape s;
+  s.rq = nq > 1024 ? 8 : (nq > 256 ? 4 : 2);
+  s.threads = std::max(32, ((nq + 32 * s.rq - 1) / (32 * s.rq)) * 32);
+  s.chunks = 1;
+  return s;
+}
+
+template <int MODE>
+cudaError_t launch_scan_m(int rq, dim3 grid, int threads, cudaStream_t st, const KfEntry* kfs, int n_kf,
+                          const QFrame* frames, int n_frames, lc_kf_result* res, int* counter, Knobs kb) {
+  switch (rq) {
+    case 2: kf_scan_kernel<2, MODE><<<grid, threads, 0, st>>>(kfs, n_kf, frames, n_frames, res, counter, kb); break;
+    case 4: kf_scan_kernel<4, MODE><<<grid, threads, 0, st>>>(kfs, n_kf, frames, n_frames, res, counter, kb); break;
+    default: kf_scan_kernel<8, MODE><<<grid, threads, 0, st>>>(kfs, n_kf, frames, n_frames, res, counter, kb); break;
+  }
+  return cudaGetLastError();
+}
+
+template <int MODE>
+int scan_occupancy(int rq, int threads) {
+  int occ = 0;
+  switch (rq) {
+    case 2: cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kf_scan_kernel<2, MODE>, threads, 0); break;
+    case 4: cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kf_scan_kernel<4, MODE>, threads, 0); break;
+    default: cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kf_scan_kernel<8, MODE>, threads, 0); break;
+  }
+  return std::max(occ, 1);
+}
+
+template <int MODE>
+cudaError_t launch_split_m(int rq, dim3 grid, int threads, cudaStream_t st, const KfEntry* kfs, int n_kf, int item0,
+                           const QFrame* frames, uint32_t* scratch, int stride, int seg_rows, Knobs kb) {
+  switch (rq) {
+    case 2: split_kernel<2, MODE><<<grid, threads, 0, st>>>(kfs, n_kf, item0, frames, scratch, stride, seg_rows, kb); break;
+    case 4: split_kernel<4, MODE><<<grid, threads, 0, st>>>(kfs, n_kf, item0, frames, scratch, stride, seg_rows, kb); break;
+    default: split_kernel<8, MODE><<<grid, threads, 0, st>>>(kfs, n_kf, item0, frames, scratch, stride, seg_rows, kb); break;
+  }
+  return cudaGetLastError();
+}
+
+struct PairOut {  // optional per-query outputs of the pair API (device pointers)
+  int32_t* train_idx = nullptr;
+  int32_t* dist = nullptr;
+  uint8_t* good = nullptr;
+  int32_t* summary = nullptr;
+};
+
+// Match n_frames query frames against n_kf keyframes (device tables) on `st`.
+// h_frames mirrors d_frames (needed for nq).  max_rows = max n over the keyframes.
+int run_match(lc_ctx* c, cudaStream_t st, const KfEntry* d_kfs, int n_kf, int max_rows, const QFrame* d_frames,
+              const QFrame* h_frames, int n_frames, lc_kf_result* d_results, const PairOut& po, Knobs kb,
+              bool force_split) {
+  const long long n_items = (long long)n_kf * n_frames;
+  if (n_items == 0) return LC_OK;
+  if (n_items > 0x7fffffffll) return fail(c, LC_ERR_INVALID, "too many (frame, keyframe) items: %lld", n_items);
+  int max_nq = 0;
+  for (int f = 0; f < n_frames; ++f) max_nq = std::max(max_nq, h_frames[f].nq);
+  const int mode = mode_of(c->cfg);
+
+  // ---- whole-keyframe scan: enough items to fill every CTA slot many times over
+  if (!force_split && max_nq <= kFusedMaxNq && max_nq > 0) {
+    const Shape sh = scan_shape(max_nq);
+    const int occ = mode == MODE_POPC ? scan_occupancy<MODE_POPC>(sh.rq, sh.threads) : scan_occupancy<MODE_CSA>(sh.rq, sh.threads);
+    const long long slots = (long long)c->num_sms * occ;
+    if (n_items >= 16 * slots) {
+      LC_TRY(ensure(c, c->d_counter, 256));
+      LC_CUDA(c, cudaMemsetAsync(c->d_counter.p, 0, sizeof(int), st));
+      const dim3 grid((unsigned)std::min<long long>(slots, n_items));
+      cudaError_t e = mode == MODE_POPC
+                          ? launch_scan_m<MODE_POPC>(sh.rq, grid, sh.threads, st, d_kfs, n_kf, d_frames, n_frames, d_results, (int*)c->d_counter.p, kb)
+                          : launch_scan_m<MODE_CSA>(sh.rq, grid, sh.threads, st, d_kfs, n_kf, d_frames, n_frames, d_results, (int*)c->d_counter.p, kb);
+      LC_CUDA(c, e);
+      c->launches += 1;
+      c->timing.kernel_launches += 1;
+      c->timing.path = 1;
+      return LC_OK;
+    }
+  }
+
+  // ---- split: (row segment, item, query chunk) grid + finalize, in batches bounded by the scratch budget
+  c->timing.path = 2;
+  if (max_nq == 0 || max_rows == 0) {  // nothing to compare: finalize alone writes the "skipped" records
+    max_nq = std::max(max_nq, 1);
+  }
+  // widest register tile (fewest LDS per pair) that still yields enough CTAs to fill the machine
+  Shape sh{};
+  int seg = kTileRows;
+  for (int rq : {8, 4, 2}) {
+    sh.rq = rq;
+    sh.threads = std::min(256, std::max(32, ((max_nq + 32 * rq - 1) / (32 * rq)) * 32));
+    sh.chunks = (max_nq + sh.threads * rq - 1) / (sh.threads * rq);
+    seg = kTileRows;
+    while (seg > 32 && n_items * ((max_rows + seg - 1) / seg) * sh.chunks < 4ll * c->num_sms) seg >>= 1;
+    if (n_items * ((max_rows + seg - 1) / seg) * sh.chunks >= 4ll * c->num_sms && seg >= 64) break;
+  }
+  const int n_seg = std::max(1, (max_rows + seg - 1) / seg);
+  const int stride = (max_nq + 3) & ~3;
+  long long batch = std::max<long long>(1, (long long)(kScratchBudgetBytes / ((size_t)stride * 4)));
+  batch = std::min<long long>(std::min<long long>(batch, 65535), n_items);
+  LC_TRY(ensure(c, c->d_scratch, (size_t)batch * stride * 4));
+  for (long long item0 = 0; item0 < n_items; item0 += batch) {
+    const int nb = (int)std::min<long long>(batch, n_items - item0);
+    LC_CUDA(c, cudaMemsetAsync(c->d_scratch.p, 0xff, (size_t)nb * stride * 4, st));
+    if (max_rows > 0) {
+      const dim3 grid(n_seg, nb, sh.chunks);
+      cudaError_t e = mode == MODE_POPC
+                          ? launch_split_m<MODE_POPC>(sh.rq, grid, sh.threads, st, d_kfs, n_kf, (int)item0, d_frames, (uint32_t*)c->d_scratch.p, stride, seg, kb)
+                          : launch_split_m<MODE_CSA>(sh.rq, grid, sh.threads, st, d_kfs, n_kf, (int)item0, d_frames, (uint32_t*)c->d_scratch.p, stride, seg, kb);
+      LC_CUDA(c, e);
+      c->launches += 1;
+      c->timing.kernel_launches += 1;
+    }
+    finalize_kernel<<<nb, 256, 0, st>>>(d_kfs, n_kf, (int)item0, d_frames, (const uint32_t*)c->d_scratch.p, stride, d_results,
+                                        po.train_idx, po.dist, po.good, po.summary, kb);
+    LC_CUDA(c, cudaGetLastError());
+    c->launches += 1;
+    c->timing.kernel_launches += 1;
+  }
+  return LC_OK;
+}
+
+int fill_best(lc_ctx* c, cudaStream_t st, uint64_t* d_best, size_t n) {
+  if (!d_best || n == 0) return LC_OK;
+  const int blocks = (int)std::min<size_t>((n + 255) / 256, 1024);
+  fill_u64_kernel<<<blocks, 256, 0, st>>>(d_best, n, ~0ull);
+  LC_CUDA(c, cudaGetLastError());
+  c->launches += 1;
+  c->timing.kernel_launches += 1;
+  return LC_OK;
+}
+
+// loop check of n_frames device-resident frames (rows concatenated at d_q) against the local store
+int loop_check_device_impl(lc_ctx* c, cudaStream_t st, int n_frames, const void* d_q, const int32_t* nq,
+                           const int32_t* cur_ids, lc_kf_result* d_results, uint64_t* d_best) {
+  if (n_frames <= 0) return LC_OK;
+  if ((uintptr_t)d_q % 16 != 0) return fail(c, LC_ERR_INVALID, "d_q must be 16-byte aligned");
+  LC_TRY(sync_kf_table(c));
+  std::vector<QFrame> hf((size_t)n_frames);
+  size_t row = 0;
+  for (int f = 0; f < n_frames; ++f) {
+    if (nq[f] < 0 || nq[f] > LC_MAX_ROWS_PER_KF) return fail(c, LC_ERR_INVALID, "nq[%d] = %d out of range", f, nq[f]);
+    hf[f] = QFrame{(const uint4*)d_q + 2 * row, nq[f], cur_ids[f], d_best ? d_best + row : nullptr};
+    row += (size_t)nq[f];
+  }
+  LC_TRY(fill_best(c, st, d_best, row));
+  const int n_kf = (int)c->h_kf.size();
+  if (n_kf == 0) return LC_OK;
+  LC_TRY(ensure(c, c->d_frames, hf.size() * sizeof(QFrame)));
+  // pageable source: the runtime stages it before returning, so `hf` may die with this frame
+  LC_CUDA(c, cudaMemcpyAsync(c->d_frames.p, hf.data(), hf.size() * sizeof(QFrame), cudaMemcpyHostToDevice, st));
+  return run_match(c, st, (const KfEntry*)c->d_kf.p, n_kf, c->max_n_local, (const QFrame*)c->d_frames.p, hf.data(), n_frames,
+                   d_results, PairOut{}, knobs_of(c->cfg), false);
+}
+
+int pair_device_impl(lc_ctx* c, cudaStream_t st, const void* d_q, int nq, const KfEntry& train, const PairOut& po) {
+  // one temporary (frame, keyframe) item; the gap test is disabled (matchFeatures has none)
+  struct {
+    KfEntry kf;
+    QFrame fr;
+  } h;
+  h.kf = train;
+  h.kf.frame_id = 0;
+  h.kf.global_row_off = 0;
+  h.fr = QFrame{(const uint4*)d_q, nq, 0, nullptr};
+  LC_TRY(ensure(c, c->d_pair, sizeof h));
+  LC_CUDA(c, cudaMemcpyAsync(c->d_pair.p, &h, sizeof h, cudaMemcpyHostToDevice, st));
+  Knobs kb = knobs_of(c->cfg);
+  kb.min_loop_gap = -(1 << 30);
+  kb.gap_strict = 0;
+  const KfEntry* d_kf = (const KfEntry*)c->d_pair.p;
+  const QFrame* d_fr = (const QFrame*)((const uint8_t*)c->d_pair.p + offsetof(decltype(h), fr));
+  return run_match(c, st, d_kf, 1, train.n, d_fr, &h.fr, 1, nullptr, po, kb, true);
+}
+
+int stage_query(lc_ctx* c, DevBuf& buf, const uint8_t* q, int64_t n, size_t stride) {
+  LC_TRY(ensure(c, buf, (size_t)std::max<int64_t>(n, 1) * LC_DESC_BYTES));
+  if (n > 0) LC_TRY(upload_rows(c, (uint8_t*)buf.p, q, n, stride));
+  return LC_OK;
+}
+
+void timing_begin(lc_ctx* c) {
+  c->timing = lc_timing{};
+  cudaEventRecord(c->ev[0], c->stream);
+}
+int timing_end(lc_ctx* c) {
+  LC_CUDA(c, cudaEventRecord(c->ev[3], c->stream));
+  LC_CUDA(c, cudaStreamSynchronize(c->stream));
+  cudaEventElapsedTime(&c->timing.h2d_ms, c->ev[0], c->ev[1]);
+  cudaEventElapsedTime(&c->timing.kernel_ms, c->ev[1], c->ev[2]);
+  cudaEventElapsedTime(&c->timing.d2h_ms, c->ev[2], c->ev[3]);
+  cudaEventElapsedTime(&c->timing.total_ms, c->ev[0], c->ev[3]);
+  return LC_OK;
+}
+
+int pair_host_impl(lc_ctx* c, int32_t nq, const KfEntry& train, int32_t* train_idx, int32_t* dist, uint8_t* good,
+                   int32_t* n_matches, int32_t* min_dist, int32_t* n_good) {
+  // device outputs: idx[nq] dist[nq] summary[2] good[nq]
+  const size_t off_dist = (size_t)nq * 4, off_sum = off_dist + (size_t)nq * 4, off_good = off_sum + 8;
+  const size_t out_bytes = off_good + (size_t)nq;
+  LC_TRY(ensure(c, c->d_out, out_bytes));
+  LC_TRY(ensure_pin_down(c, out_bytes));
+  uint8_t* d = (uint8_t*)c->d_out.p;
+  PairOut po{(int32_t*)d, (int32_t*)(d + off_dist), d + off_good, (int32_t*)(d + off_sum)};
+  LC_CUDA(c, cudaEventRecord(c->ev[1], c->stream));
+  LC_TRY(pair_device_impl(c, c->stream, c->d_q.p, nq, train, po));
+  LC_CUDA(c, cudaEventRecord(c->ev[2], c->stream));
+  LC_CUDA(c, cudaMemcpyAsync(c->pin_down, d, out_bytes, cudaMemcpyDeviceToHost, c->stream));
+  LC_TRY(timing_end(c));
+  const uint8_t* h = c->pin_down;
+  if (train_idx) memcpy(train_idx, h, (size_t)nq * 4);
+  if (dist) memcpy(dist, h + off_dist, (size_t)nq * 4);
+  if (good) memcpy(good, h + off_good, (size_t)nq);
+  int32_t sum[2];
+  memcpy(sum, h + off_sum, 8);
+  if (n_matches) *n_matches = nq;
+  if (min_dist) *min_dist = sum[0];
+  if (n_good) *n_good = sum[1];
+  return LC_OK;
+}
+
+void empty_pair(int32_t* n_matches, int32_t* min_dist, int32_t* n_good) {
+  if (n_matches) *n_matches = 0;
+  if (min_dist) *min_dist = -1;
+  if (n_good) *n_good = 0;
+}
+
+int check_rows(lc_ctx* c, const char* what, const uint8_t* p, int32_t n, size_t stride) {
+  if (n < 0 || n > LC_MAX_ROWS_PER_KF) return fail(c, LC_ERR_INVALID, "%s: n = %d outside [0, %d]", what, n, LC_MAX_ROWS_PER_KF);
+  if (n > 0 && !p) return fail(c, LC_ERR_INVALID, "%s: NULL descriptors with n = %d", what, n);
+  if (n > 0 && stride < LC_DESC_BYTES) return fail(c, LC_ERR_INVALID, "%s: row_stride %zu < 32", what, stride);
+  return LC_OK;
+}
+
+}  // namespace
+
+// =================================================================== extern "C"
+#define LC_API extern "C" __attribute__((visibility("default")))
+#define LC_GUARD_BEGIN try {
+#define LC_GUARD_END(c)                                          \
+  }                                                              \
+  catch (const std::bad_alloc&) { return fail((c), LC_ERR_NOMEM, "host allocation failed"); } \
+  catch (const std::exception& e) { return fail((c), LC_ERR_INVALID, "%s", e.what()); }       \
+  catch (...) { return fail((c), LC_ERR_INVALID, "unknown C++ exception"); }
+
+LC_API int32_t lc_abi_version(void) { return LC_ABI_VERSION; }
+
+LC_API void lc_default_config(lc_config* g) {
+  if (!g) return;
+  memset(g, 0, sizeof *g);
+  g->struct_size = sizeof *g;
+  g->device = 0;
+  g->loop_threshold = 0.7;  // include/loop_closing.hpp:31
+  g->min_loop_gap = 30;
+  g->min_good = 50;
+  g->filter_floor = 0;
+  g->filter_strict = 0;
+  g->min_init = -1;
+  g->gap_strict = 0;
+  g->thr_inclusive = 0;
+  g->shard_rank = 0;
+  g->shard_world = 1;
+  g->kernel = LC_KERNEL_AUTO;
+  g->slab_rows = 0;
+}
+
+LC_API const char* lc_last_error(const lc_ctx* c) { return c ? c->err.c_str() : g_create_error.c_str(); }
+
+LC_API void lc_destroy(lc_ctx* c) {
+  if (!c) return;
+  cudaSetDevice(c->cfg.device);
+  if (c->stream) cudaStreamSynchronize(c->stream);
+  for (void* p : c->slabs) cudaFree(p);
+  for (DevBuf* b : {&c->d_kf, &c->d_q, &c->d_t, &c->d_results, &c->d_best, &c->d_scratch, &c->d_frames, &c->d_pair, &c->d_out, &c->d_counter})
+    if (b->p) cudaFree(b->p);
+  if (c->pin_up) cudaFreeHost(c->pin_up);
+  if (c->pin_down) cudaFreeHost(c->pin_down);
+  for (auto& e : c->ev) if (e) cudaEventDestroy(e);
+  for (auto& e : c->pin_ev) if (e) cudaEventDestroy(e);
+  if (c->stream) cudaStreamDestroy(c->stream);
+  delete c;
+}
+
+LC_API int32_t lc_create(const lc_config* cfg, lc_ctx** out) {
+  if (!out) return fail(nullptr, LC_ERR_INVALID, "out is NULL");
+  *out = nullptr;
+  lc_ctx* c = nullptr;
+  LC_GUARD_BEGIN
+  lc_config g;
+  lc_default_config(&g);
+  if (cfg) {
+    if (cfg->struct_size != sizeof(lc_config)) return fail(nullptr, LC_ERR_INVALID, "lc_config.struct_size %u != %zu", cfg->struct_size, sizeof(lc_config));
+    g = *cfg;
+  }
+  LC_TRY(validate(nullptr, g));
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0)
+    return fail(nullptr, LC_ERR_CUDA, "no usable CUDA device (%s); this library has no CPU fallback", cudaGetErrorString(e));
+  if (g.device < 0 || g.device >= ndev) return fail(nullptr, LC_ERR_INVALID, "device %d not in [0, %d)", g.device, ndev);
+  c = new lc_ctx();
+  c->cfg = g;
+  c->slab_rows = g.slab_rows > 0 ? g.slab_rows : kDefaultSlabRows;
+  auto bail = [&](const char* what, cudaError_t err) {
+    fail(nullptr, LC_ERR_CUDA, "%s: %s", what, cudaGetErrorString(err));
+    lc_destroy(c);
+    return (int32_t)LC_ERR_CUDA;
+  };
+  if ((e = cudaSetDevice(g.device)) != cudaSuccess) return bail("cudaSetDevice", e);
+  cudaDeviceProp prop;
+  if ((e = cudaGetDeviceProperties(&prop, g.device)) != cudaSuccess) return bail("cudaGetDeviceProperties", e);
+  if (prop.major != 10) {
+    fail(nullptr, LC_ERR_CUDA, "device %d is sm_%d%d; liblc_b200 carries sm_100a code only", g.device, prop.major, prop.minor);
+    lc_destroy(c);
+    return LC_ERR_CUDA;
+  }
+  c->num_sms = prop.multiProcessorCount;
+  if ((e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail("cudaStreamCreate", e);
+  for (auto& ev : c->ev) if ((e = cudaEventCreate(&ev)) != cudaSuccess) return bail("cudaEventCreate", e);
+  for (auto& ev : c->pin_ev) {
+    if ((e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming)) != cudaSuccess) return bail("cudaEventCreate", e);
+    cudaEventRecord(ev, c->stream);
+  }
+  if ((e = cudaMallocHost((void**)&c->pin_up, 2 * kPinHalfBytes)) != cudaSuccess) return bail("cudaMallocHost", e);
+  *out = c;
+  return LC_OK;
+  LC_GUARD_END(nullptr)
+}
+
+LC_API int32_t lc_get_config(const lc_ctx* c, lc_config* out) {
+  if (!c || !out) return LC_ERR_INVALID;
+  *out = c->cfg;
+  return LC_OK;
+}
+
+LC_API int32_t lc_set_params(lc_ctx* c, const lc_config* g) {
+  if (!c) return LC_ERR_INVALID;
+  if (!g || g->struct_size != sizeof(lc_config)) return fail(c, LC_ERR_INVALID, "bad lc_config");
+  if (g->device != c->cfg.device || g->shard_rank != c->cfg.shard_rank || g->shard_world != c->cfg.shard_world)
+    return fail(c, LC_ERR_INVALID, "device and sharding cannot change after lc_create");
+  LC_TRY(validate(c, *g));
+  const int64_t slab = c->cfg.slab_rows;
+  c->cfg = *g;
+  c->cfg.slab_rows = slab;
+  return LC_OK;
+}
+
+// ------------------------------------------------------------------- store
+LC_API int32_t lc_db_append(lc_ctx* c, int32_t frame_id, const uint8_t* desc, int32_t n, size_t stride, int64_t* kf_index) {
+  if (!c) return LC_ERR_INVALID;
+  LC_GUARD_BEGIN
+  LC_CUDA(c, cudaSetDevice(c->cfg.device));
+  return store_append(c, frame_id, desc, n, stride, false, kf_index);
+  LC_GUARD_END(c)
+}
+
+LC_API int32_t lc_db_append_many(lc_ctx* c, int32_t count, const int32_t* frame_ids, const int32_t* n_rows, const uint8_t* const* desc) {
+  if (!c) return LC_ERR_INVALID;
+  if (count < 0 || (count > 0 && (!frame_ids || !n_rows || !desc))) return fail(c, LC_ERR_INVALID, "bad arguments");
+  LC_GUARD_BEGIN
+  LC_CUDA(c, cudaSetDevice(c->cfg.device));
+  for (int32_t i = 0; i < count; ++i) LC_TRY(store_append(c, frame_ids[i], desc[i], n_rows[i], LC_DESC_BYTES, false, nullptr));
+  return LC_OK;
+  LC_GUARD_END(c)
+}
+
+// device-resident source rows: d_rows holds the rows of the OWNED keyframes of this call, back to back
+LC_API int32_t lc_db_append_many_device(lc_ctx* c, int32_t count, const int32_t* frame_ids, const int32_t* n_rows, const void* d_rows) {
+  if (!c) return LC_ERR_INVALID;
+  if (count < 0 || (count > 0 && (!frame_ids || !n_rows))) return fail(c, LC_ERR_INVALID, "bad arguments");
+  LC_GUARD_BEGIN
+  LC_CUDA(c, cudaSetDevice(c->cfg.device));
+  const uint8_t* p = (const uint8_t*)d_rows;
+  for (int32_t i = 0; i < count; ++i) {
+    const bool own = (c->g_kf % c->cfg.shard_world) == c->cfg.shard_rank;
+    LC_TRY(store_append(c, frame_ids[i], own ? p : nullptr, n_rows[i], LC_DESC_BYTES, true, nullptr));
+    if (own) p += (size_t)n_rows[i] * LC_DESC_BYTES;
+  }
+  return LC_OK;
+  LC_GUARD_END(c)
+}
+
+LC_API int32_t lc_db_size(const lc_ctx* c, int64_t* n_kf, int64_t* n_rows, int64_t* n_local_kf, int64_t* n_local_rows) {
+  if (!c) return LC_ERR_INVALID;
+  if (n_kf) *n_kf = c->g_kf;
+  if (n_rows) *n_rows = c->g_rows;
+  if (n_local_kf) *n_local_kf = (int64_t)c->h_kf.size();
+  if (n_local_rows) *n_local_rows = c->l_rows;
+  return LC_OK;
+}
+
+LC_API int32_t lc_db_clear(lc_ctx* c) {
+  if (!c) return LC_ERR_INVALID;
+  LC_GUARD_BEGIN
+  LC_CUDA(c, cudaSetDevice(c->cfg.device));
+  LC_CUDA(c, cudaStreamSynchronize(c->stream));
+  for (void* p : c->slabs) cudaFree(p);
+  c->slabs.clear();
+  c->last_slab_cap = c->last_slab_used = 0;
+  c->h_kf.clear();
+  c->h_kf_global.clear();
+  c->d_kf_synced = 0;
+  c->g_kf = c->g_rows = c->l_rows = 0;
+  c->max_n_local = 0;
+  return LC_OK;
+  LC_GUARD_END(c)
+}
+
+static int find_local(lc_ctx* c, int64_t kf_index, size_t* slot) {
+  if (kf_index < 0 || kf_index >= c->g_kf) return fail(c, LC_ERR_INVALID, "kf_index %lld not in [0, %lld)", (long long)kf_index, (long long)c->g_kf);
+  if (kf_index % c->cfg.shard_world != c->cfg.shard_rank) return fail(c, LC_ERR_INVALID, "keyframe %lld is not stored on shard %d", (long long)kf_index, c->cfg.shard_rank);
+  *slot = (size_t)(kf_index / c->cfg.shard_world);
+  return LC_OK;
+}
+
+LC_API int32_t lc_db_read(lc_ctx* c, int64_t kf_index, uint8_t* desc_out, int32_t cap_rows, int32_t* n, int32_t* frame_id) {
+  if (!c) return LC_ERR_INVALID;
+  LC_GUARD_BEGIN
+  LC_CUDA(c, cudaSetDevice(c->cfg.device));
+  size_t s;
+  LC_TRY(find_local(c, kf_index, &s));
+  const KfEntry& e = c->h_kf[s];
+  if (n) *n = e.n;
+  if (frame_id) *frame_id = e.frame_id;
+  if (desc_out) {
+    if (cap_rows < e.n) return fail(c, LC_ERR_CAPACITY, "cap_rows %d < %d", cap_rows, e.n);
+    if (e.n > 0) {
+      LC_CUDA(c, cudaMemcpyAsync(desc_out, e.rows, (size_t)e.n * LC_DESC_BYTES, cudaMemcpyDeviceToHost, c->stream));
+      LC_CUDA(c, cudaStreamSynchronize(c->stream));
+    }
+  }
+  return LC_OK;
+  LC_GUARD_END(c)
+}
+
+// file format: "LCB200DB" u32 version, u32 shard_rank, u32 shard_world, i64 g_kf, i64 g_rows, i64 n_local,
+// then per local keyframe {i64 global_index, i64 global_row_off, i32 frame_id, i32 n}, then the rows.
+LC_API int32_t lc_db_save(lc_ctx* c, const char* path) {
+  if (!c || !path) return LC_ERR_INVALID;
+  LC_GUARD_BEGIN
+  LC_CUDA(c, cudaSetDevice(c->cfg.device));
+  LC_CUDA(c, cudaStreamSynchronize(c->stream));
+  FILE* f = fopen(path, "wb");
+  if (!f) return fail(c, LC_ERR_IO, "cannot open %s for writing", path);
+  bool ok = true;
+  auto W = [&](const void* p, size_t n) { ok = ok && fwrite(p, 1, n, f) == n; };
+  const uint32_t hdr[3] = {1u, (uint32_t)c->cfg.shard_rank, (uint32_t)c->cfg.shard_world};
+  const int64_t cnt[3] = {c->g_kf, c->g_rows, (int64_t)c->h_kf.size()};
+  W("LCB200DB", 8);
+  W(hdr, sizeof hdr);
+  W(cnt, sizeof cnt);
+  for (size_t i = 0; i < c->h_kf.size(); ++i) {
+    const int64_t a[2] = {c->h_kf_global[i], c->h_kf[i].global_row_off};
+    const int32_t b[2] = {c->h_kf[i].frame_id, c->h_kf[i].n};
+    W(a, sizeof a);
+    W(b, sizeof b);
+  }
+  std::vector<uint8_t> buf;
+  for (size_t i = 0; i < c->h_kf.size() && ok; ++i) {
+    const KfEntry& e = c->h_kf[i];
+    if (e.n == 0) continue;
+    buf.resize((size_t)e.n * LC_DESC_BYTES);
+    if (cudaMemcpy(buf.data(), e.rows, buf.size(), cudaMemcpyDeviceToHost) != cudaSuccess) {
+      fclose(f);
+      return fail(c, LC_ERR_CUDA, "device read failed while saving");
+    }
+    W(buf.data(), buf.size());
+  }
+  ok = (fclose(f) == 0) && ok;
+  if (!ok) return fail(c, LC_ERR_IO, "short write to %s", path);
+  return LC_OK;
+  LC_GUARD_END(c)
+}
+
+LC_API int32_t lc_db_load(lc_ctx* c, const char* path) {
+  if (!c || !path) return LC_ERR_INVALID;
+  LC_GUARD_BEGIN
+  LC_CUDA(c, cudaSetDevice(c->cfg.device));
+  if (c->g_kf != 0) return fail(c, LC_ERR_INVALID, "lc_db_load needs an empty store (call lc_db_clear)");
+  FILE* f = fopen(path, "rb");
+  if (!f) return fail(c, LC_ERR_IO, "cannot open %s", path);
+  bool ok = true;
+  auto R = [&](void* p, size_t n) { ok = ok && fread(p, 1, n, f) == n; };
+  char magic[8];
+  uint32_t hdr[3];
+  int64_t cnt[3];
+  R(magic, 8);
+  R(hdr, sizeof hdr);
+  R(cnt, sizeof cnt);
+  if (!ok || memcmp(magic, "LCB200DB", 8) != 0 || hdr[0] != 1u) {
+    fclose(f);
+    return fail(c, LC_ERR_IO, "%s is not a liblc_b200 store file", path);
+  }
+  if ((int32_t)hdr[1] != c->cfg.shard_rank || (int32_t)hdr[2] != c->cfg.shard_world) {
+    fclose(f);
+    return fail(c, LC_ERR_INVALID, "%s holds shard %u/%u, context is %d/%d", path, hdr[1], hdr[2], c->cfg.shard_rank, c->cfg.shard_world);
+  }
+  struct Rec { int64_t gi, off; int32_t fid, n; };
+  std::vector<Rec> recs((size_t)cnt[2]);
+  for (auto& r : recs) {
+    R(&r.gi, 16);
+    R(&r.fid, 8);
+  }
+  std::vector<uint8_t> buf;
+  for (size_t i = 0; i < recs.size() && ok; ++i) {
+    const Rec& r = recs[i];
+    if (r.n < 0 || r.n > LC_MAX_ROWS_PER_KF) { ok = false; break; }
+    buf.resize((size_t)r.n * LC_DESC_BYTES);
+    if (r.n) R(buf.data(), buf.size());
+    if (!ok) break;
+    uint4* rows = nullptr;
+    int rc = slab_alloc(c, r.n, &rows);
+    if (rc == LC_OK && r.n) rc = upload_rows(c, (uint8_t*)rows, buf.data(), r.n, LC_DESC_BYTES);
+    if (rc != LC_OK) { fclose(f); return rc; }
+    c->h_kf.push_back(KfEntry{rows, r.n, r.fid, r.off});
+    c->h_kf_global.push_back(r.gi);
+    c->l_rows += r.n;
+    c->max_n_local = std::max(c->max_n_local, r.n);
+  }
+  fclose(f);
+  if (!ok) {
+    lc_db_clear(c);
+    return fail(c, LC_ERR_IO, "%s is truncated or corrupt", path);
+  }
+  c->g_kf = cnt[0];
+  c->g_rows = cnt[1];
+  LC_CUDA(c, cudaStreamSynchronize(c->stream));
+  return LC_OK;
+  LC_GUARD_END(c)
+}
+
+// ------------------------------------------------------------------- matchFeatures
+LC_API int32_t lc_match_pair(lc_ctx* c, const uint8_t* q, int32_t nq, size_t qs, const uint8_t* t, int32_t nt, size_t ts,
+                             int32_t* train_idx, int32_t* dist, uint8_t* good, int32_t* n_matches, int32_t* min_dist, int32_t* n_good) {
+  if (!c) return LC_ERR_INVALID;
+  LC_GUARD_BEGIN
+  LC_TRY(check_rows(c, "query", q, nq, qs));
+  LC_TRY(check_rows(c, "train", t, nt, ts));
+  if (nq == 0 || nt == 0) {  // cv::BFMatcher returns no matches when either side is empty
+    empty_pair(n_matches, min_dist, n_good);
+    return LC_OK;
+  }
+  LC_CUDA(c, cudaSetDevice(c->cfg.device));
+  timing_begin(c);
+  LC_TRY(stage_query(c, c->d_q, q, nq, qs));
+  LC_TRY(stage_query(c, c->d_t, t, nt, ts));
+  KfEntry train{(const uint4*)c->d_t.p, nt, 0, 0};
+  return pair_host_impl(c, nq, train, train_idx, dist, good, n_matches, min_dist, n_good);
+  LC_GUARD_END(c)
+}
+
+LC_API int32_t lc_match_vs_keyframe(lc_ctx* c, const uint8_t* q, int32_t nq, size_t qs, int64_t kf_index, int32_t* train_idx,
+                                    int32_t* dist, uint8_t* good, int32_t* n_matches, int32_t* min_dist, int32_t* n_good) {
+  if (!c) return LC_ERR_INVALID;
+  LC_GUARD_BEGIN
+  LC_TRY(check_rows(c, "query", q, nq, qs));
+  size_t s;
+  LC_TRY(find_local(c, kf_index, &s));
+  const KfEntry train = c->h_kf[s];
+  if (nq == 0 || train.n == 0) {
+    empty_pair(n_matches, min_dist, n_good);
+    return LC_OK;
+  }
+  LC_CUDA(c, cudaSetDevice(c->cfg.device));
+  timing_begin(c);
+  LC_TRY(stage_query(c, c->d_q, q, nq, qs));
+  return pair_host_impl(c, nq, train, train_idx, dist, good, n_matches, min_dist, n_good);
+  LC_GUARD_END(c)
+}
+
+LC_API int32_t lc_match_pair_device(lc_ctx* c, const void* d_q, int32_t nq, const void* d_t, int32_t nt, int32_t* d_train_idx,
+                                    int32_t* d_dist, uint8_t* d_good, int32_t* d_summary, void* cuda_stream) {
+  if (!c) return LC_ERR_INVALID;
+  LC_GUARD_BEGIN
+  if (nq < 0 || nt < 0 || nq > LC_MAX_ROWS_PER_KF || nt > LC_MAX_ROWS_PER_KF) return fail(c, LC_ERR_INVALID, "row count out of range");
+  if (((uintptr_t)d_q | (uintptr_t)d_t) % 16 != 0) return fail(c, LC_ERR_INVALID, "device rows must be 16-byte aligned");
+  LC_CUDA(c, cudaSetDevice(c->cfg.device));
+  cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : c->stream;
+  if (nq == 0 || nt == 0) {
+    if (d_summary) {
+      const int32_t s[2] = {-1, 0};
+      LC_CUDA(c, cudaMemcpyAsync(d_summary, s, sizeof s, cudaMemcpyHostToDevice, st));
+    }
+    return LC_OK;
+  }
+  KfEntry train{(const uint4*)d_t, nt, 0, 0};
+  return pair_device_impl(c, st, d_q, nq, train, PairOut{d_train_idx, d_dist, d_good, d_summary});
+  LC_GUARD_END(c)
+}
+
+// ------------------------------------------------------------------- detectLoops
+LC_API int32_t lc_loop_check_batch_device(lc_ctx* c, int32_t n_frames, const void* d_q, const int32_t* nq, const int32_t* cur_ids,
+                                          lc_kf_result* d_results, uint64_t* d_best, void* cuda_stream) {
+  if (!c) return LC_ERR_INVALID;
+  LC_GUARD_BEGIN
+  if (n_frames < 0 || (n_frames > 0 && (!nq || !cur_ids))) return fail(c, LC_ERR_INVALID, "bad arguments");
+  if (!d_results && !c->h_kf.empty() && n_frames > 0) return fail(c, LC_ERR_INVALID, "d_results is NULL");
+  LC_CUDA(c, cudaSetDevice(c->cfg.device));
+  cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : c->stream;
+  return loop_check_device_impl(c, st, n_frames, d_q, nq, cur_ids, d_results, d_best);
+  LC_GUARD_END(c)
+}
+
+LC_API int32_t lc_loop_check_device(lc_ctx* c, const void* d_q, int32_t nq, int32_t cur_id, lc_kf_result* d_results,
+                                    uint64_t* d_best, void* cuda_stream) {
+  return lc_loop_check_batch_device(c, 1, d_q, &nq, &cur_id, d_results, d_best, cuda_stream);
+}
+
+LC_API int32_t lc_loop_check_batch(lc_ctx* c, int32_t n_frames, const uint8_t* const* q, const int32_t* nq, const int32_t* cur_ids,
+                                   lc_kf_result* results, int64_t results_cap, uint64_t* best_packed) {
+  if (!c) return LC_ERR_INVALID;
+  LC_GUARD_BEGIN
+  if (n_frames < 0 || (n_frames > 0 && (!q || !nq || !cur_ids))) return fail(c, LC_ERR_INVALID, "bad arguments");
+  const int64_t n_kf = (int64_t)c->h_kf.size();
+  const int64_t n_res = n_kf * n_frames;
+  if (n_res > 0 && (!results || results_cap < n_res)) return fail(c, LC_ERR_CAPACITY, "results_cap %lld < %lld", (long long)results_cap, (long long)n_res);
+  int64_t rows = 0;
+  for (int f = 0; f < n_frames; ++f) {
+    LC_TRY(check_rows(c, "query", q[f], nq[f], LC_DESC_BYTES));
+    rows += nq[f];
+  }
+  if (n_frames == 0) return LC_OK;
+  LC_CUDA(c, cudaSetDevice(c->cfg.device));
+  timing_begin(c);
+  LC_TRY(ensure(c, c->d_q, (size_t)std::max<int64_t>(rows, 1) * LC_DESC_BYTES));
+  int64_t r0 = 0;
+  for (int f = 0; f < n_frames; ++f) {
+    if (nq[f] > 0) LC_TRY(upload_rows(c, (uint8_t*)c->d_q.p + (size_t)r0 * LC_DESC_BYTES, q[f], nq[f], LC_DESC_BYTES));
+    r0 += nq[f];
+  }
+  const size_t res_bytes = (size_t)n_res * sizeof(lc_kf_result), best_bytes = best_packed ? (size_t)rows * 8 : 0;
+  LC_TRY(ensure(c, c->d_results, std::max<size_t>(res_bytes, 16)));
+  LC_TRY(ensure(c, c->d_best, std::max<size_t>(best_bytes, 16)));
+  LC_TRY(ensure_pin_down(c, res_bytes + best_bytes + 16));
+  LC_CUDA(c, cudaEventRecord(c->ev[1], c->stream));
+  LC_TRY(loop_check_device_impl(c, c->stream, n_frames, c->d_q.p, nq, cur_ids, (lc_kf_result*)c->d_results.p,
+                                best_packed ? (uint64_t*)c->d_best.p : nullptr));
+  LC_CUDA(c, cudaEventRecord(c->ev[2], c->stream));
+  if (res_bytes) LC_CUDA(c, cudaMemcpyAsync(c->pin_down, c->d_results.p, res_bytes, cudaMemcpyDeviceToHost, c->stream));
+  if (best_bytes) LC_CUDA(c, cudaMemcpyAsync(c->pin_down + res_bytes, c->d_best.p, best_bytes, cudaMemcpyDeviceToHost, c->stream));
+  LC_TRY(timing_end(c));
+  if (res_bytes) memcpy(results, c->pin_down, res_bytes);
+  if (best_bytes) memcpy(best_packed, c->pin_down + res_bytes, best_bytes);
+  return LC_OK;
+  LC_GUARD_END(c)
+}
+
+LC_API int32_t lc_loop_check(lc_ctx* c, const uint8_t* q, int32_t nq, size_t qs, int32_t cur_id, lc_kf_result* results,
+                             int64_t results_cap, int64_t* n_results, uint64_t* best_packed) {
+  if (!c) return LC_ERR_INVALID;
+  LC_GUARD_BEGIN
+  LC_TRY(check_rows(c, "query", q, nq, qs));
+  if (n_results) *n_results = (int64_t)c->h_kf.size();
+  if (qs == LC_DESC_BYTES || nq == 0) return lc_loop_check_batch(c, 1, &q, &nq, &cur_id, results, results_cap, best_packed);
+  std::vector<uint8_t> packed((size_t)nq * LC_DESC_BYTES);  // strided cv::Mat: make the rows contiguous
+  for (int32_t i = 0; i < nq; ++i) memcpy(packed.data() + (size_t)i * LC_DESC_BYTES, q + (size_t)i * qs, LC_DESC_BYTES);
+  const uint8_t* p = packed.data();
+  return lc_loop_check_batch(c, 1, &p, &nq, &cur_id, results, results_cap, best_packed);
+  LC_GUARD_END(c)
+}
+
+LC_API int32_t lc_select_candidates(const lc_ctx* c, const lc_kf_result* results, int64_t n_results, int32_t nq, int32_t cur_id,
+                                    lc_loop_candidate* out, int64_t out_cap, int64_t* n_out) {
+  if (!c || n_results < 0 || (n_results > 0 && !results)) return LC_ERR_INVALID;
+  int64_t n = 0;
+  for (int64_t k = 0; k < n_results; ++k) {
+    const lc_kf_result& r = results[k];
+    if (r.n_good < 0) continue;
+    const int32_t denom = std::min(nq, r.n_kf);
+    if (denom <= 0) continue;
+    const double sim = (double)r.n_good / (double)denom;  // README.md:126
+    const bool over = c->cfg.thr_inclusive ? (sim >= c->cfg.loop_threshold) : (sim > c->cfg.loop_threshold);
+    if (over && r.n_good >= c->cfg.min_good) {  // README.md:123-124
+      if (out && n < out_cap) out[n] = lc_loop_candidate{cur_id, r.frame_id, r.n_good, sim};
+      ++n;
+    }
+  }
+  if (n_out) *n_out = n;
+  return (out && n > out_cap) ? LC_ERR_CAPACITY : LC_OK;
+}
+
+LC_API int32_t lc_detect_loops(lc_ctx* c, const uint8_t* q, int32_t nq, size_t qs, int32_t cur_id, lc_loop_candidate* out,
+                               int64_t out_cap, int64_t* n_out) {
+  if (!c) return LC_ERR_INVALID;
+  LC_GUARD_BEGIN
+  if (c->cfg.shard_world != 1) return fail(c, LC_ERR_INVALID, "lc_detect_loops needs an unsharded context; gather lc_loop_check records and call lc_select_candidates");
+  std::vector<lc_kf_result> res(c->h_kf.size());
+  int64_t n = 0;
+  LC_TRY(lc_loop_check(c, q, nq, qs, cur_id, res.data(), (int64_t)res.size(), &n, nullptr));
+  const int rc = lc_select_candidates(c, res.data(), n, nq, cur_id, out, out_cap, n_out);
+  if (rc == LC_ERR_CAPACITY) return fail(c, rc, "out_cap %lld too small", (long long)out_cap);
+  return rc;
+  LC_GUARD_END(c)
+}
+
+// ------------------------------------------------------------------- introspection
+LC_API int32_t lc_get_last_timing(const lc_ctx* c, lc_timing* out) {
+  if (!c || !out) return LC_ERR_INVALID;
+  *out = c->timing;
+  return LC_OK;
+}
+LC_API int64_t lc_launch_count(const lc_ctx* c) { return c ? c->launches : 0; }
+LC_API int32_t lc_synchronize(lc_ctx* c) {
+  if (!c) return LC_ERR_INVALID;
+  LC_CUDA(c, cudaSetDevice(c->cfg.device));
+  LC_CUDA(c, cudaStreamSynchronize(c->stream));
+  return LC_OK;
+}
