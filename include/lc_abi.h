@@ -178,7 +178,8 @@ int32_t lc_detect_loops(lc_ctx* ctx, const uint8_t* q, int32_t nq, size_t q_stri
                         lc_loop_candidate* out, int64_t out_cap, int64_t* n_out);
 
 /* ---- device-pointer variants: everything already in HBM, asynchronous on `cuda_stream`
- *      (a cudaStream_t; NULL = the context's own stream).  d_q: contiguous 32-byte rows, 16-byte
+ *      (a cudaStream_t; NULL = the context's own non-blocking stream - pass cudaStreamLegacy (0x1) to
+ *      mean the legacy default stream).  d_q: contiguous 32-byte rows, 16-byte
  *      aligned.  Used for multi-GPU merging (NCCL min all-reduce of d_best_packed, all-gather of
  *      d_results) and for kernel-only timing.  d_best_packed may be NULL. ---- */
 int32_t lc_loop_check_device(lc_ctx* ctx, const void* d_q, int32_t nq, int32_t current_frame_id,

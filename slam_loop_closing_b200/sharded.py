@@ -1,0 +1,131 @@
+"""Keyframe-sharded loop check across GPUs: one process per GPU, torch.distributed for the exchange.
+
+Partitioning: keyframe k lives on rank k % world (append-time round robin), never
+replicated.  A loop check broadcasts nothing but the 64 KB query (every rank already holds it), runs
+the local scan, then does the path's one real exchange:
+    * all_reduce(MIN) of the per-query packed best (dist << 32 | global_row) - an integer min, so the
+      merge is bit-exact and order-independent (NCCL over NVLink/NVSwitch on GPUs);
+    * all_gather of the per-keyframe records, re-interleaved into global keyframe order.
+global_row counts rows of all keyframes in insertion order, so the merged best reproduces OpenCV's
+multi-image tie-break (lowest image, then lowest row) whatever the world size.
+
+torch is plumbing here (device buffers, the current CUDA stream, the process group).  The compute is
+liblc_b200's lc_loop_check_batch_device; a `shard` object with the same three methods can be swapped in
+(the CPU tests of the merge logic do that with the oracle over gloo).
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from . import _native
+
+_SENTINEL = (-1, 0, -1, -1)  # padding record for ranks with one keyframe fewer
+
+
+class NativeShard:
+    """This rank's shard: an lc_ctx bound to the rank's GPU, outputs in torch CUDA tensors."""
+
+    def __init__(self, rank, world, device, **cfg):
+        self.device = torch.device("cuda", device)
+        self.ctx = _native.Context(device=device, shard_rank=rank, shard_world=world, **cfg)
+
+    def append(self, frame_id, desc, n):
+        if desc is None:
+            self.ctx.db_append_meta(frame_id, n)
+        else:
+            self.ctx.db_append(frame_id, desc)
+
+    def local_keyframes(self):
+        return self.ctx.db_size()["local_keyframes"]
+
+    def to_device(self, q_rows: np.ndarray) -> torch.Tensor:
+        t = torch.from_numpy(np.ascontiguousarray(q_rows, np.uint8).reshape(-1, 32))
+        return t.pin_memory().to(self.device, non_blocking=True) if t.numel() else t.to(self.device)
+
+    def loop_check(self, d_q: torch.Tensor, nq, cur_ids, slots):
+        """d_q: (sum nq, 32) uint8 CUDA tensor.  Returns (records int32 [F, slots, 4], best int64 [sum nq])."""
+        F = len(nq)
+        rec = torch.empty((F, slots, 4), dtype=torch.int32, device=self.device)
+        rec[:] = torch.tensor(_SENTINEL, dtype=torch.int32, device=self.device)
+        nloc = self.local_keyframes()
+        best = torch.empty(int(np.sum(nq)), dtype=torch.int64, device=self.device)
+        local = torch.empty((F, nloc, 4), dtype=torch.int32, device=self.device) if nloc != slots else rec
+        # NULL means "the context's own stream" in the C ABI; torch's default stream is handle 0, so name it
+        # explicitly (cudaStreamLegacy == 0x1) to stay ordered with the torch ops around this call
+        stream = torch.cuda.current_stream(self.device).cuda_stream or 1
+        self.ctx.loop_check_batch_device(d_q.data_ptr() if d_q.numel() else None, nq, cur_ids,
+                                         local.data_ptr() if nloc else None, best.data_ptr() if best.numel() else None,
+                                         stream)
+        if local is not rec and nloc:
+            rec[:, :nloc] = local
+        return rec, best
+
+
+class ShardedLoopDB:
+    """Every rank calls every method with the same arguments (SPMD)."""
+
+    def __init__(self, group=None, device=None, shard=None, **cfg):
+        self.group = group
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        if shard is None:
+            device = device if device is not None else torch.cuda.current_device()
+            shard = NativeShard(self.rank, self.world, device, **cfg)
+        self.shard = shard
+        self.n_keyframes = 0
+
+    def owns(self, k):
+        return k % self.world == self.rank
+
+    def append(self, frame_id, desc, n=None):
+        """desc may be None on ranks that do not own this keyframe (then n is required)."""
+        k = self.n_keyframes
+        own = self.owns(k)
+        if own and desc is None:
+            raise ValueError(f"rank {self.rank} owns keyframe {k} but got no descriptors")
+        self.shard.append(frame_id, desc if own else None, len(desc) if desc is not None else int(n))
+        self.n_keyframes += 1
+        return k
+
+    def loop_check(self, queries, current_frame_ids):
+        """queries: list of (nq,32) uint8 arrays (or one CUDA uint8 tensor of concatenated rows with
+        `nq` given via a tuple (tensor, nq_list)).  Returns (records [F][K] KF_RESULT in global keyframe
+        order, best list of uint64 arrays)."""
+        if isinstance(queries, tuple):
+            d_q, nq = queries
+            nq = np.asarray(nq, np.int32)
+        else:
+            nq = np.array([len(q) for q in queries], np.int32)
+            rows = np.concatenate([np.asarray(q, np.uint8).reshape(-1, 32) for q in queries]) if len(queries) else \
+                np.zeros((0, 32), np.uint8)
+            d_q = self.shard.to_device(rows)
+        cur = np.asarray(current_frame_ids, np.int32)
+        rec, best = self.merged_device(d_q, nq, cur)
+        K = self.n_keyframes
+        rec_np = rec.cpu().numpy().reshape(len(nq), -1, 4)[:, :K]
+        out = np.zeros((len(nq), K), _native.KF_RESULT)
+        for i, name in enumerate(("frame_id", "n_kf", "min_dist", "n_good")):
+            out[name] = rec_np[:, :, i]
+        b = best.cpu().numpy().view(np.uint64)
+        offs = np.concatenate([[0], np.cumsum(nq)])
+        return out, [b[offs[i]:offs[i + 1]] for i in range(len(nq))]
+
+    def merged_device(self, d_q, nq, cur):
+        """Device-resident result of the sharded check: (records int32 [F, slots*world, 4] in global keyframe
+        order (padded with sentinels past K), best int64 [sum nq]).  The exchange happens here."""
+        slots = (self.n_keyframes + self.world - 1) // self.world
+        rec, best = self.shard.loop_check(d_q, nq, cur, slots)
+        if self.world == 1:
+            return rec, best
+        if best.numel():
+            # dist <= 256 keeps the packed value positive, so the signed int64 min is the uint64 min
+            dist.all_reduce(best, op=dist.ReduceOp.MIN, group=self.group)
+        F = rec.shape[0]
+        gathered = torch.empty((self.world * F, slots, 4), dtype=rec.dtype, device=rec.device)
+        dist.all_gather_into_tensor(gathered, rec.contiguous(), group=self.group)
+        gathered = gathered.view(self.world, F, slots, 4)
+        # [world, F, slots, 4] -> [F, slots, world, 4]: global keyframe k = slot * world + rank
+        merged = gathered.permute(1, 2, 0, 3).reshape(rec.shape[0], slots * self.world, 4)
+        return merged, best

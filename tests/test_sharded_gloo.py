@@ -1,0 +1,119 @@
+"""CPU tier, world_size 2 and 3 over gloo: the host-side shard/merge logic of slam_loop_closing_b200.sharded
+(round-robin ownership, sentinel padding, all_reduce(MIN) of the packed best, all_gather + re-interleave).
+The per-shard compute is swapped for the CPU oracle here (the product shard needs a GPU); the merge code
+under test is exactly the code that runs over NCCL on the GPUs."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+import datagen
+from oracle import c_oracle
+from oracle.params import Params
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+class OracleShard:
+    """Test double with NativeShard's interface, computing on the CPU oracle."""
+
+    def __init__(self, rank, world, p):
+        self.rank, self.world, self.p = rank, world, p
+        self.kfs, self.meta = [], []  # local rows; (frame_id, n, global_row_off) for local keyframes
+        self.g_rows = 0
+        self.g_kf = 0
+
+    def append(self, frame_id, desc, n):
+        if self.g_kf % self.world == self.rank:
+            self.kfs.append(np.asarray(desc, np.uint8).reshape(-1, 32))
+            self.meta.append((frame_id, n, self.g_rows))
+        self.g_kf += 1
+        self.g_rows += n
+
+    def local_keyframes(self):
+        return len(self.kfs)
+
+    def to_device(self, rows):
+        return torch.from_numpy(np.ascontiguousarray(rows))
+
+    def loop_check(self, d_q, nq, cur_ids, slots):
+        F = len(nq)
+        rec = torch.tensor([-1, 0, -1, -1], dtype=torch.int32).repeat(F, slots, 1)
+        best = torch.full((int(np.sum(nq)),), -1, dtype=torch.int64)
+        rows = d_q.numpy()
+        off = 0
+        for f in range(F):
+            q = rows[off:off + nq[f]]
+            b = np.full(nq[f], np.iinfo(np.uint64).max, np.uint64)
+            for s, (kf, (fid, n, goff)) in enumerate(zip(self.kfs, self.meta)):
+                res, bk = c_oracle.loop_check(q, kf, [n], [fid], int(cur_ids[f]), self.p)
+                rec[f, s] = torch.tensor([res[0]["frame_id"], res[0]["n_kf"], res[0]["min_dist"], res[0]["n_good"]])
+                hit = bk != np.iinfo(np.uint64).max
+                bk = np.where(hit, bk + np.uint64(goff), bk)
+                b = np.minimum(b, bk)
+            best[off:off + nq[f]] = torch.from_numpy(b.view(np.int64))
+            off += nq[f]
+        return rec, best
+
+
+def _case():
+    q0 = datagen.low_entropy(150, 1)  # ties that straddle shards
+    qs = [q0, datagen.low_entropy(90, 2), np.zeros((0, 32), np.uint8)]
+    curs = [40, 25, 40]
+    ns = np.random.default_rng(3).integers(0, 60, 23)
+    kfs = [datagen.low_entropy(int(n), 100 + i) for i, n in enumerate(ns)]
+    return qs, curs, kfs, list(range(len(kfs))), Params(min_loop_gap=5, loop_threshold=0.15)
+
+
+def _worker(rank, world, port, ret):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from slam_loop_closing_b200.sharded import ShardedLoopDB
+        qs, curs, kfs, fids, p = _case()
+        db = ShardedLoopDB(shard=OracleShard(rank, world, p))
+        for k, (fid, kf) in enumerate(zip(fids, kfs)):
+            db.append(fid, kf if db.owns(k) else None, n=len(kf))
+        rec, best = db.loop_check(qs, curs)
+        if rank == 0:
+            ret["rec"], ret["best"] = rec, [b.copy() for b in best]
+    finally:
+        dist.destroy_process_group()
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_sharded_merge_equals_unsharded_over_gloo(world):
+    qs, curs, kfs, fids, p = _case()
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_worker, args=(world, _free_port(), ret), nprocs=world, join=True)
+    db = np.concatenate(kfs)
+    for f, (q, cur) in enumerate(zip(qs, curs)):
+        want_res, want_best = c_oracle.loop_check(q, db, [len(k) for k in kfs], fids, cur, p)
+        np.testing.assert_array_equal(ret["rec"][f], want_res)
+        np.testing.assert_array_equal(ret["best"][f], want_best)
+
+
+def test_world_one_needs_no_process_group():
+    from slam_loop_closing_b200.sharded import ShardedLoopDB
+    qs, curs, kfs, fids, p = _case()
+    db = ShardedLoopDB(shard=OracleShard(0, 1, p))
+    for fid, kf in zip(fids, kfs):
+        db.append(fid, kf)
+    rec, best = db.loop_check(qs[:1], curs[:1])
+    want_res, want_best = c_oracle.loop_check(qs[0], np.concatenate(kfs), [len(k) for k in kfs], fids, curs[0], p)
+    np.testing.assert_array_equal(rec[0], want_res)
+    np.testing.assert_array_equal(best[0], want_best)
