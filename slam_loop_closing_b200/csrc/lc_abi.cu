@@ -126,7 +126,7 @@ int ensure_pin_down(lc_ctx* c, size_t bytes) {
 }
 
 Knobs knobs_of(const lc_config& g) {
-  return Knobs{g.min_loop_gap, g.gap_strict, g.filter_floor, g.filter_strict, g.min_init};
+  return Knobs{g.min_loop_gap, g.gap_strict, g.filter_floor, g.filter_strict, g.min_init, 1u << kKeyShift};
 }
 
 int mode_of(const lc_config& g) { return g.kernel == LC_KERNEL_POPC ? MODE_POPC : MODE_CSA; }

@@ -53,6 +53,7 @@ struct QFrame {  // one query frame
 
 struct Knobs {
   int32_t min_loop_gap, gap_strict, filter_floor, filter_strict, min_init;
+  uint32_t key_unit;  // always 1 << kKeyShift; a runtime value on purpose (see ham_key)
 };
 
 // ---------------------------------------------------------------- PTX helpers (mbarrier + bulk copy)
@@ -92,12 +93,16 @@ __device__ __forceinline__ void full_add(uint32_t a, uint32_t b, uint32_t c, uin
 
 // key = (hamming(q, t) << 20) + row.  The adds are IMADs (fma pipe) so the alu pipe only carries
 // the LOP3s and the min; row is warp-uniform.
+// `unit` is 1 << kKeyShift held in a register the compiler cannot see through (it comes from a kernel
+// argument): with an immediate power of two ptxas strength-reduces the last IMAD to LEA, which lands
+// on the alu pipe that already carries the 16 LOP3s and is the binding pipe of the carry-save form.
 template <int MODE>
-__device__ __forceinline__ uint32_t ham_key(const uint32_t (&q)[8], const uint4& a, const uint4& b, uint32_t row) {
+__device__ __forceinline__ uint32_t ham_key(const uint32_t (&q)[8], const uint4& a, const uint4& b, uint32_t row,
+                                            uint32_t unit) {
   if (MODE == MODE_POPC) {
     uint32_t d = __popc(q[0] ^ a.x) + __popc(q[1] ^ a.y) + __popc(q[2] ^ a.z) + __popc(q[3] ^ a.w) +
                  __popc(q[4] ^ b.x) + __popc(q[5] ^ b.y) + __popc(q[6] ^ b.z) + __popc(q[7] ^ b.w);
-    return (d << kKeyShift) + row;
+    return d * unit + row;
   } else {
     // Spelled as explicit LOP3s: left to itself nvcc re-associates the tree into ~22 LOP3 per pair.
     const uint32_t x0 = q[0] ^ a.x, x1 = q[1] ^ a.y, x2 = q[2] ^ a.z, x3 = q[3] ^ a.w;
@@ -109,10 +114,10 @@ __device__ __forceinline__ uint32_t ham_key(const uint32_t (&q)[8], const uint4&
     full_add(s1, s2, x6, ones, c3);
     full_add(c1, c2, c3, twos, fours);
     uint32_t key = row;
-    key = __popc(fours) * (4u << kKeyShift) + key;
-    key = __popc(twos) * (2u << kKeyShift) + key;
-    key = __popc(ones) * (1u << kKeyShift) + key;
-    key = __popc(x7) * (1u << kKeyShift) + key;
+    key = __popc(fours) * (4 * unit) + key;
+    key = __popc(twos) * (2 * unit) + key;
+    key = __popc(ones) * unit + key;
+    key = __popc(x7) * unit + key;
     return key;
   }
 }
@@ -120,22 +125,22 @@ __device__ __forceinline__ uint32_t ham_key(const uint32_t (&q)[8], const uint4&
 // scan `cnt` staged rows (row index of tile[0] is `row0`), updating the RQ running keys
 template <int RQ, int MODE>
 __device__ __forceinline__ void scan_rows(const uint4* __restrict__ tile, int cnt, uint32_t row0,
-                                          const uint32_t (&q)[RQ][8], uint32_t (&best)[RQ]) {
+                                          const uint32_t (&q)[RQ][8], uint32_t (&best)[RQ], uint32_t unit) {
   int r = 0;
 #pragma unroll 1
   for (; r + 2 <= cnt; r += 2) {
     const uint4 a0 = tile[2 * r], b0 = tile[2 * r + 1], a1 = tile[2 * r + 2], b1 = tile[2 * r + 3];
 #pragma unroll
     for (int s = 0; s < RQ; ++s) {
-      const uint32_t k0 = ham_key<MODE>(q[s], a0, b0, row0 + r);
-      const uint32_t k1 = ham_key<MODE>(q[s], a1, b1, row0 + r + 1);
+      const uint32_t k0 = ham_key<MODE>(q[s], a0, b0, row0 + r, unit);
+      const uint32_t k1 = ham_key<MODE>(q[s], a1, b1, row0 + r + 1, unit);
       best[s] = min(best[s], min(k0, k1));  // VIMNMX3.U32
     }
   }
   if (r < cnt) {
     const uint4 a0 = tile[2 * r], b0 = tile[2 * r + 1];
 #pragma unroll
-    for (int s = 0; s < RQ; ++s) best[s] = min(best[s], ham_key<MODE>(q[s], a0, b0, row0 + r));
+    for (int s = 0; s < RQ; ++s) best[s] = min(best[s], ham_key<MODE>(q[s], a0, b0, row0 + r, unit));
   }
 }
 
@@ -248,7 +253,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1)
       const uint32_t st = seq % kStages;
       const int cnt = min(kTileRows, kf.n - t * kTileRows);
       mbar_wait(&full[st], (seq / kStages) & 1);
-      scan_rows<RQ, MODE>(tiles[st], cnt, (uint32_t)(t * kTileRows), q, best);
+      scan_rows<RQ, MODE>(tiles[st], cnt, (uint32_t)(t * kTileRows), q, best, kb.key_unit);
       __syncthreads();  // every thread is done with this stage before it is refilled
       if (tid == 0 && t + kStages < n_tiles) {
         const int t2 = t + kStages;
@@ -311,7 +316,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1)
   for (int s = 0; s < RQ; ++s) best[s] = 0xffffffffu;
   __syncthreads();  // barrier init visible before anyone waits on it
   mbar_wait(&full, 0);
-  scan_rows<RQ, MODE>(tile, cnt, (uint32_t)row0, q, best);
+  scan_rows<RQ, MODE>(tile, cnt, (uint32_t)row0, q, best, kb.key_unit);
   uint32_t* dst = scratch + (size_t)blockIdx.y * scratch_stride;
 #pragma unroll
   for (int s = 0; s < RQ; ++s) {
