@@ -49,7 +49,9 @@ typedef enum lc_status {
 typedef enum lc_kernel {
   LC_KERNEL_AUTO = 0, /* library default (the measured-fastest bit-exact integer path) */
   LC_KERNEL_POPC = 1, /* 8 x (XOR, POPC) per pair: the naive integer-popc formulation */
-  LC_KERNEL_CSA = 2   /* carry-save adder tree: 16 LOP3 + 4 POPC per pair, same result */
+  LC_KERNEL_CSA = 2,  /* carry-save adder tree: 16 LOP3 + 4 POPC per pair, same result */
+  LC_KERNEL_TENSOR = 3 /* tcgen05.mma kind::i8 on +1/-1 expanded bits (dot = 256 - 2*hamming) + arg-max epilogue, same
+                          result; problems too small to fill the GPU use the CSA kernels */
 } lc_kernel;
 
 /* Parameters of the path.  Defaults (lc_default_config) follow the reference header and README;
@@ -99,7 +101,7 @@ typedef struct lc_timing {
   float d2h_ms;    /* device -> pinned results */
   float total_ms;  /* first H2D to last D2H on the stream */
   int32_t kernel_launches;
-  int32_t path;    /* 1 = whole-keyframe scan kernel, 2 = split kernel + finalize */
+  int32_t path;    /* 1 = whole-keyframe scan kernel, 2 = split kernel + finalize, 3 = tensor-core kernel + finalize */
 } lc_timing;
 
 int32_t lc_abi_version(void);

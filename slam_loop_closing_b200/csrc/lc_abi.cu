@@ -16,6 +16,7 @@
 #include <vector>
 
 #include "lc_kernels.cuh"
+#include "lc_tensor.cuh"
 
 using namespace lc;
 
@@ -63,7 +64,7 @@ struct lc_ctx {
   int pin_half = 0;
   uint8_t* pin_down = nullptr;
   size_t pin_down_cap = 0;
-  DevBuf d_q, d_t, d_results, d_best, d_scratch, d_frames, d_pair, d_out, d_counter;
+  DevBuf d_q, d_t, d_results, d_best, d_scratch, d_frames, d_pair, d_out, d_counter, d_qimg, d_ablocks;
 
   lc_timing timing{};
   int64_t launches = 0;
@@ -129,12 +130,12 @@ Knobs knobs_of(const lc_config& g) {
   return Knobs{g.min_loop_gap, g.gap_strict, g.filter_floor, g.filter_strict, g.min_init, 1u << kKeyShift};
 }
 
-int mode_of(const lc_config& g) { return g.kernel == LC_KERNEL_POPC ? MODE_POPC : MODE_CSA; }
+int mode_of(const lc_config& g) { return g.kernel == LC_KERNEL_POPC ? MODE_POPC : MODE_CSA; }  // the tensor path falls back to CSA for tiny problems
 
 int validate(lc_ctx* c, const lc_config& g) {
   if (g.shard_world < 1 || g.shard_rank < 0 || g.shard_rank >= g.shard_world)
     return fail(c, LC_ERR_INVALID, "shard_rank %d / shard_world %d invalid", g.shard_rank, g.shard_world);
-  if (g.kernel < LC_KERNEL_AUTO || g.kernel > LC_KERNEL_CSA) return fail(c, LC_ERR_INVALID, "unknown kernel %d", g.kernel);
+  if (g.kernel < LC_KERNEL_AUTO || g.kernel > LC_KERNEL_TENSOR) return fail(c, LC_ERR_INVALID, "unknown kernel %d", g.kernel);
   if (g.slab_rows < 0) return fail(c, LC_ERR_INVALID, "slab_rows < 0");
   if (g.min_loop_gap < -(1 << 30) || g.min_loop_gap > (1 << 30)) return fail(c, LC_ERR_INVALID, "min_loop_gap out of range");
   return LC_OK;
@@ -257,12 +258,12 @@ int scan_occupancy(int rq, int threads) {
 }
 
 template <int MODE>
-cudaError_t launch_split_m(int rq, dim3 grid, int threads, cudaStream_t st, const KfEntry* kfs, int n_kf, int item0,
+cudaError_t launch_split_m(int rq, dim3 grid, int threads, cudaStream_t st, const KfEntry* kfs, int k0, int kc,
                            const QFrame* frames, uint32_t* scratch, int stride, int seg_rows, Knobs kb) {
   switch (rq) {
-    case 2: split_kernel<2, MODE><<<grid, threads, 0, st>>>(kfs, n_kf, item0, frames, scratch, stride, seg_rows, kb); break;
-    case 4: split_kernel<4, MODE><<<grid, threads, 0, st>>>(kfs, n_kf, item0, frames, scratch, stride, seg_rows, kb); break;
-    default: split_kernel<8, MODE><<<grid, threads, 0, st>>>(kfs, n_kf, item0, frames, scratch, stride, seg_rows, kb); break;
+    case 2: split_kernel<2, MODE><<<grid, threads, 0, st>>>(kfs, k0, kc, frames, scratch, stride, seg_rows, kb); break;
+    case 4: split_kernel<4, MODE><<<grid, threads, 0, st>>>(kfs, k0, kc, frames, scratch, stride, seg_rows, kb); break;
+    default: split_kernel<8, MODE><<<grid, threads, 0, st>>>(kfs, k0, kc, frames, scratch, stride, seg_rows, kb); break;
   }
   return cudaGetLastError();
 }
@@ -287,7 +288,7 @@ int run_match(lc_ctx* c, cudaStream_t st, const KfEntry* d_kfs, int n_kf, int ma
   const int mode = mode_of(c->cfg);
 
   // ---- whole-keyframe scan: enough items to fill every CTA slot many times over
-  if (!force_split && max_nq <= kFusedMaxNq && max_nq > 0) {
+  if (!force_split && c->cfg.kernel != LC_KERNEL_TENSOR && max_nq <= kFusedMaxNq && max_nq > 0) {
     const Shape sh = scan_shape(max_nq);
     const int occ = mode == MODE_POPC ? scan_occupancy<MODE_POPC>(sh.rq, sh.threads) : scan_occupancy<MODE_CSA>(sh.rq, sh.threads);
     const long long slots = (long long)c->num_sms * occ;
@@ -306,7 +307,49 @@ int run_match(lc_ctx* c, cudaStream_t st, const KfEntry* d_kfs, int n_kf, int ma
     }
   }
 
-  // ---- split: (row segment, item, query chunk) grid + finalize, in batches bounded by the scratch budget
+  // ---- tensor cores: int8 GEMM + arg-max (lc_tensor.cuh) when there is a machine's worth of work
+  if (c->cfg.kernel == LC_KERNEL_TENSOR && !force_split && max_nq > 0 && max_rows > 0) {
+    std::vector<tc::ABlock> blocks;
+    for (int f = 0; f < n_frames; ++f)
+      for (int q0 = 0; q0 < h_frames[f].nq; q0 += tc::kQPerCta)
+        blocks.push_back(tc::ABlock{nullptr, f, q0});
+    const int n_ab = (int)blocks.size();
+    if ((long long)n_ab * n_kf >= c->num_sms) {
+      LC_TRY(ensure(c, c->d_qimg, (size_t)n_ab * tc::kABytes));
+      LC_TRY(ensure(c, c->d_ablocks, (size_t)n_ab * sizeof(tc::ABlock)));
+      for (int i = 0; i < n_ab; ++i) blocks[i].img = (const uint8_t*)c->d_qimg.p + (size_t)i * tc::kABytes;
+      LC_CUDA(c, cudaMemcpyAsync(c->d_ablocks.p, blocks.data(), (size_t)n_ab * sizeof(tc::ABlock), cudaMemcpyHostToDevice, st));
+      tc::expand_queries_kernel<<<n_ab, 256, 0, st>>>((const tc::ABlock*)c->d_ablocks.p, d_frames, (uint8_t*)c->d_qimg.p);
+      LC_CUDA(c, cudaGetLastError());
+      static bool attr_set = false;
+      if (!attr_set) {
+        LC_CUDA(c, cudaFuncSetAttribute(tc::tensor_match_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kSmemAlloc));
+        attr_set = true;
+      }
+      const int stride = (max_nq + 3) & ~3;
+      long long kc_max = std::max<long long>(1, (long long)(kScratchBudgetBytes / ((size_t)stride * 4)) / n_frames);
+      kc_max = std::min<long long>(kc_max, n_kf);
+      LC_TRY(ensure(c, c->d_scratch, (size_t)kc_max * n_frames * stride * 4));
+      const int n_slots = std::max(1, c->num_sms / n_ab);
+      c->launches += 1;
+      c->timing.kernel_launches += 1;
+      for (int k0 = 0; k0 < n_kf; k0 += (int)kc_max) {
+        const int kc = (int)std::min<long long>(kc_max, n_kf - k0);
+        tc::tensor_match_kernel<<<n_ab * std::min(n_slots, kc), tc::kThreads, tc::kSmemAlloc, st>>>(
+            d_kfs, k0, kc, d_frames, (const tc::ABlock*)c->d_ablocks.p, n_ab, (uint32_t*)c->d_scratch.p, stride, kb);
+        LC_CUDA(c, cudaGetLastError());
+        finalize_kernel<<<kc * n_frames, 256, 0, st>>>(d_kfs, n_kf, k0, kc, d_frames, (const uint32_t*)c->d_scratch.p, stride,
+                                                       d_results, po.train_idx, po.dist, po.good, po.summary, kb);
+        LC_CUDA(c, cudaGetLastError());
+        c->launches += 2;
+        c->timing.kernel_launches += 2;
+      }
+      c->timing.path = 3;
+      return LC_OK;
+    }
+  }
+
+  // ---- split: (row segment, frame x keyframe, query chunk) grid + finalize, in batches bounded by the scratch budget
   c->timing.path = 2;
   if (max_nq == 0 || max_rows == 0) {  // nothing to compare: finalize alone writes the "skipped" records
     max_nq = std::max(max_nq, 1);
@@ -324,22 +367,24 @@ int run_match(lc_ctx* c, cudaStream_t st, const KfEntry* d_kfs, int n_kf, int ma
   }
   const int n_seg = std::max(1, (max_rows + seg - 1) / seg);
   const int stride = (max_nq + 3) & ~3;
-  long long batch = std::max<long long>(1, (long long)(kScratchBudgetBytes / ((size_t)stride * 4)));
-  batch = std::min<long long>(std::min<long long>(batch, 65535), n_items);
-  LC_TRY(ensure(c, c->d_scratch, (size_t)batch * stride * 4));
-  for (long long item0 = 0; item0 < n_items; item0 += batch) {
-    const int nb = (int)std::min<long long>(batch, n_items - item0);
+  // batches of keyframes [k0, k0 + kc) x all frames, bounded by the scratch budget and gridDim.y
+  long long kc_max = std::max<long long>(1, (long long)(kScratchBudgetBytes / ((size_t)stride * 4)) / n_frames);
+  kc_max = std::min<long long>(std::min<long long>(kc_max, std::max(1, 65535 / n_frames)), n_kf);
+  LC_TRY(ensure(c, c->d_scratch, (size_t)kc_max * n_frames * stride * 4));
+  for (int k0 = 0; k0 < n_kf; k0 += (int)kc_max) {
+    const int kc = (int)std::min<long long>(kc_max, n_kf - k0);
+    const int nb = kc * n_frames;
     LC_CUDA(c, cudaMemsetAsync(c->d_scratch.p, 0xff, (size_t)nb * stride * 4, st));
     if (max_rows > 0) {
       const dim3 grid(n_seg, nb, sh.chunks);
       cudaError_t e = mode == MODE_POPC
-                          ? launch_split_m<MODE_POPC>(sh.rq, grid, sh.threads, st, d_kfs, n_kf, (int)item0, d_frames, (uint32_t*)c->d_scratch.p, stride, seg, kb)
-                          : launch_split_m<MODE_CSA>(sh.rq, grid, sh.threads, st, d_kfs, n_kf, (int)item0, d_frames, (uint32_t*)c->d_scratch.p, stride, seg, kb);
+                          ? launch_split_m<MODE_POPC>(sh.rq, grid, sh.threads, st, d_kfs, k0, kc, d_frames, (uint32_t*)c->d_scratch.p, stride, seg, kb)
+                          : launch_split_m<MODE_CSA>(sh.rq, grid, sh.threads, st, d_kfs, k0, kc, d_frames, (uint32_t*)c->d_scratch.p, stride, seg, kb);
       LC_CUDA(c, e);
       c->launches += 1;
       c->timing.kernel_launches += 1;
     }
-    finalize_kernel<<<nb, 256, 0, st>>>(d_kfs, n_kf, (int)item0, d_frames, (const uint32_t*)c->d_scratch.p, stride, d_results,
+    finalize_kernel<<<nb, 256, 0, st>>>(d_kfs, n_kf, k0, kc, d_frames, (const uint32_t*)c->d_scratch.p, stride, d_results,
                                         po.train_idx, po.dist, po.good, po.summary, kb);
     LC_CUDA(c, cudaGetLastError());
     c->launches += 1;
@@ -499,7 +544,7 @@ LC_API void lc_destroy(lc_ctx* c) {
   cudaSetDevice(c->cfg.device);
   if (c->stream) cudaStreamSynchronize(c->stream);
   for (void* p : c->slabs) cudaFree(p);
-  for (DevBuf* b : {&c->d_kf, &c->d_q, &c->d_t, &c->d_results, &c->d_best, &c->d_scratch, &c->d_frames, &c->d_pair, &c->d_out, &c->d_counter})
+  for (DevBuf* b : {&c->d_kf, &c->d_q, &c->d_t, &c->d_results, &c->d_best, &c->d_scratch, &c->d_frames, &c->d_pair, &c->d_out, &c->d_counter, &c->d_qimg, &c->d_ablocks})
     if (b->p) cudaFree(b->p);
   if (c->pin_up) cudaFreeHost(c->pin_up);
   if (c->pin_down) cudaFreeHost(c->pin_down);

@@ -286,17 +286,17 @@ __global__ void __launch_bounds__(kMaxThreads, 1)
 }
 
 // ---------------------------------------------------------------- split kernel + finalize
-// grid = (row segments, items, query chunks).  Each CTA scans `seg_rows` rows of one keyframe for
-// blockDim.x * RQ queries and atomically folds its keys into scratch[item * scratch_stride + i].
+// grid = (row segments, frames x keyframes [k0, k0 + kc), query chunks).  Each CTA scans `seg_rows` rows of
+// one keyframe for blockDim.x * RQ queries and atomically folds its keys into
+// scratch[(frame * kc + k - k0) * scratch_stride + i].
 template <int RQ, int MODE>
 __global__ void __launch_bounds__(kMaxThreads, 1)
-    split_kernel(const KfEntry* __restrict__ kfs, int n_kf, int item0, const QFrame* __restrict__ frames,
+    split_kernel(const KfEntry* __restrict__ kfs, int k0, int kc, const QFrame* __restrict__ frames,
                  uint32_t* __restrict__ scratch, int scratch_stride, int seg_rows, Knobs kb) {
   __shared__ __align__(128) uint4 tile[kTileRows * 2];
   __shared__ __align__(8) uint64_t full;
   const int tid = threadIdx.x, nt = blockDim.x;
-  const int item = item0 + blockIdx.y;
-  const int f = item / n_kf, k = item - f * n_kf;
+  const int f = blockIdx.y / kc, k = k0 + (blockIdx.y - f * kc);
   const QFrame fr = frames[f];
   const KfEntry kf = kfs[k];
   const int row0 = blockIdx.x * seg_rows;
@@ -325,16 +325,16 @@ __global__ void __launch_bounds__(kMaxThreads, 1)
   }
 }
 
-// one CTA per item: reduce the scratch keys of one (frame, keyframe) match.
+// one CTA per (frame, keyframe in [k0, k0 + kc)): reduce the scratch keys of one match; results[frame * n_kf + k].
 // Optional per-query outputs (pair API): train_idx, dist, good; summary = {min_dist, n_good}.
 __global__ void __launch_bounds__(256)
-    finalize_kernel(const KfEntry* __restrict__ kfs, int n_kf, int item0, const QFrame* __restrict__ frames,
+    finalize_kernel(const KfEntry* __restrict__ kfs, int n_kf, int k0, int kc, const QFrame* __restrict__ frames,
                     const uint32_t* __restrict__ scratch, int scratch_stride, lc_kf_result* __restrict__ results,
                     int32_t* __restrict__ train_idx, int32_t* __restrict__ dist, uint8_t* __restrict__ good,
                     int32_t* __restrict__ summary, Knobs kb) {
   __shared__ int red[8];
-  const int item = item0 + blockIdx.x;
-  const int f = item / n_kf, k = item - f * n_kf;
+  const int f = blockIdx.x / kc, k = k0 + (blockIdx.x - f * kc);
+  const int item = f * n_kf + k;
   const QFrame fr = frames[f];
   const KfEntry kf = kfs[k];
   const int tid = threadIdx.x;

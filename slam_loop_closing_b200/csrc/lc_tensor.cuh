@@ -1,0 +1,343 @@
+// lc_tensor.cuh - Hamming matching on the 5th-generation tensor cores (tcgen05.mma kind::i8, TMEM).
+//
+// Identity: with descriptor bits mapped to int8 +1 / -1,  dot(q, t) = 256 - 2 * hamming(q, t), so
+// argmin_j hamming == argmax_j dot and the whole match is a 128 x N x 256 int8 GEMM tile followed by a
+// row-wise arg-max.  All values are small integers, s32 accumulation is exact, the result is bit-identical
+// to the popc kernels (same key, same tie-break).
+//
+// Why this shape:
+//   * tcgen05.mma has no 1-bit kind and mma.sync b1 is emulated on sm_100a; kind::i8 at M=128 runs
+//     8192 MAC/clk/SM = 32 descriptor pairs/clk/SM, 16x the POPC pipe.
+//   * A (queries) is RESIDENT: one CTA owns up to 512 queries, expanded once by expand_queries_kernel
+//     into the exact 128B-swizzled K-major smem image (4 tiles x 32 KiB) and pulled in with 1-D TMA bulk
+//     copies.  Streaming A per tile would need ~32 B/clk/SM of L2 bandwidth chip-wide.
+//   * B (keyframe rows) is expanded IN the kernel from the 32-byte packed rows (so the store stays
+//     32 B/row in HBM): 4 expander warps turn 192 rows into a 48 KiB swizzled tile, double buffered.
+//   * D lives in TMEM (2 stages x 192 columns); 4 epilogue warps read their lane quadrant with
+//     tcgen05.ld.32x32b and fold 192 columns into one key per row: 1 IMAD + 1/2 VIMNMX3 per pair.
+//   * one elected thread issues the MMAs; mbarriers + tcgen05.commit connect the three roles.
+// Output: one u32 key (dist << 20 | row) per (frame, keyframe, query) into the scratch that
+// finalize_kernel reduces - the same contract as split_kernel.
+#pragma once
+#include "lc_kernels.cuh"
+
+namespace lc {
+namespace tc {
+
+constexpr int kQTile = 128;                 // UMMA M
+constexpr int kQTilesPerCta = 4;            // resident A tiles
+constexpr int kQPerCta = kQTile * kQTilesPerCta;
+constexpr int kTN = 192;                    // train rows per B tile (UMMA N, multiple of 16)
+constexpr int kATileBytes = kQTile * 256;   // 32 KiB: 2 K-blocks x 128 rows x 128 B
+constexpr int kBTileBytes = kTN * 256;      // 48 KiB
+constexpr int kABytes = kQTilesPerCta * kATileBytes;
+constexpr int kSmemBytes = kABytes + 2 * kBTileBytes + 256;  // + barriers
+constexpr int kSmemAlloc = kSmemBytes + 1024;                // manual 1024-B alignment
+constexpr int kThreads = 288;               // warps 0-3 epilogue, 4-7 expanders, 8 MMA issuer
+constexpr int kAccStride = 256;             // TMEM columns between the two accumulator stages
+constexpr int kTmemCols = 512;
+
+struct ABlock {          // one resident query block: 512 queries of one frame
+  const uint8_t* img;    // expanded smem image (kABytes), written by expand_queries_kernel
+  int32_t frame;
+  int32_t q0;
+};
+
+// ---------------------------------------------------------------- bit -> int8 expansion
+// nibble (4 descriptor bits) -> 4 bytes, bit set -> -1 (0xFF), clear -> +1 (0x01)
+__device__ __forceinline__ uint32_t expand_nibble(uint32_t n) {
+  const uint32_t s = (n * 0x00204081u) & 0x01010101u;  // bit i -> byte i (0/1); the partial products never overlap
+  return s * 0xFEu + 0x01010101u;                      // 0 -> 0x01, 1 -> 0xFF, no carries between bytes
+}
+// 16 bits -> one 16-byte swizzle chunk
+__device__ __forceinline__ uint4 expand_half(uint32_t h) {
+  return make_uint4(expand_nibble(h & 15u), expand_nibble((h >> 4) & 15u), expand_nibble((h >> 8) & 15u),
+                    expand_nibble((h >> 12) & 15u));
+}
+// byte offset of (row r, 32-bit descriptor word w) inside a K-major SWIZZLE_128B tile of `rows` rows:
+// [K-block = w / 4][row][128 B], 16-byte chunk index XOR (row & 7)  (Swizzle<3,4,3>)
+__device__ __forceinline__ void tile_offsets(int rows, int r, int w, uint32_t& off0, uint32_t& off1) {
+  const uint32_t base = (uint32_t)(w >> 2) * (uint32_t)rows * 128u + (uint32_t)r * 128u;
+  const uint32_t j0 = (uint32_t)(w & 3) * 2u, x = (uint32_t)(r & 7);
+  off0 = base + ((j0 ^ x) << 4);
+  off1 = base + (((j0 + 1u) ^ x) << 4);
+}
+
+// one launch per loop check: every (frame, 512-query block) gets its A image in global memory
+__global__ void expand_queries_kernel(const ABlock* __restrict__ blocks, const QFrame* __restrict__ frames, uint8_t* img_base) {
+  const ABlock ab = blocks[blockIdx.x];
+  const QFrame fr = frames[ab.frame];
+  uint8_t* img = img_base + (size_t)blockIdx.x * kABytes;
+  for (int idx = threadIdx.x; idx < kQPerCta * 8; idx += blockDim.x) {
+    const int ql = idx >> 3, w = idx & 7, q = ab.q0 + ql;
+    const uint32_t bits = q < fr.nq ? __ldg(reinterpret_cast<const uint32_t*>(fr.q) + (size_t)q * 8 + w) : 0u;
+    uint32_t o0, o1;
+    tile_offsets(kQTile, ql & (kQTile - 1), w, o0, o1);
+    uint8_t* tile = img + (size_t)(ql / kQTile) * kATileBytes;
+    *reinterpret_cast<uint4*>(tile + o0) = expand_half(bits & 0xffffu);
+    *reinterpret_cast<uint4*>(tile + o1) = expand_half(bits >> 16);
+  }
+}
+
+// ---------------------------------------------------------------- PTX: tcgen05 / mbarrier helpers
+__device__ __forceinline__ bool mbar_try(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// bounded wait: a protocol bug must trap, not hang the GPU
+__device__ __forceinline__ void mbar_wait_guard(uint64_t* bar, uint32_t parity) {
+  for (uint32_t spins = 0; !mbar_try(bar, parity); ++spins)
+    if (spins > (1u << 24)) __trap();
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(ncols) : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem]^T, int8 x int8 -> s32, issued by ONE thread
+__device__ __forceinline__ void umma_i8(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n\t}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(0u)
+      : "memory");
+}
+// mbarrier arrives once every tcgen05 op issued so far by this thread has completed
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (version 1): 8-row groups 1024 B apart
+__device__ __forceinline__ uint64_t smem_desc(uint32_t saddr) {
+  return (uint64_t)((saddr & 0x3ffffu) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) |
+         ((uint64_t)2 << 61);
+}
+// s8 x s8 -> s32, both K-major, M = 128, N = n
+__device__ __forceinline__ uint32_t instr_desc(int n) {
+  return (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(kQTile >> 4) << 24);
+}
+// this warp's 32 TMEM lanes x 32 consecutive columns -> 32 registers per thread
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, int (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// Fold this thread's row of one accumulator stage (cnt valid columns) into a key
+//   max_c (dot[c] * 2^20 - c):  the maximum picks the largest dot product, then the lowest column.
+// Not inlined: the body is ~600 instructions and is called from four unrolled sites.
+__device__ __noinline__ int fold_accumulator(uint32_t taddr, int cnt, int unit) {
+  int tkey = (int)0x80000000;
+#pragma unroll
+  for (int c = 0; c < kTN / 32; ++c) {
+    if (c * 32 < cnt) {
+      int v[32];
+      tmem_ld32(taddr + c * 32, v);
+      tmem_ld_wait();
+      if ((c + 1) * 32 <= cnt) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 2)
+          tkey = max(tkey, max(v[j] * unit - (c * 32 + j), v[j + 1] * unit - (c * 32 + j + 1)));
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (c * 32 + j < cnt) tkey = max(tkey, v[j] * unit - (c * 32 + j));
+      }
+    }
+  }
+  return tkey;
+}
+
+// ---------------------------------------------------------------- the kernel
+// grid.x = n_ablocks * n_slots; CTA (a, slot) matches A-block a against keyframes k0 + slot, + n_slots, ...
+// scratch[(frame * kc + (k - k0)) * stride + q] = dist << 20 | row  for every compared (frame, k, q).
+__global__ void __launch_bounds__(kThreads, 1)
+    tensor_match_kernel(const KfEntry* __restrict__ kfs, int k0, int kc, const QFrame* __restrict__ frames,
+                        const ABlock* __restrict__ blocks, int n_ablocks, uint32_t* __restrict__ scratch, int scratch_stride,
+                        Knobs kb) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + kABytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kABytes + 2 * kBTileBytes);
+  uint64_t* a_full = bars;          // 1 arrival + tx bytes
+  uint64_t* b_full = bars + 1;      // [2] 128 expander arrivals
+  uint64_t* b_empty = bars + 3;     // [2] 1 commit
+  uint64_t* acc_full = bars + 5;    // [2] 1 commit
+  uint64_t* acc_empty = bars + 7;   // [2] 128 epilogue arrivals
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int a = blockIdx.x % n_ablocks, slot = blockIdx.x / n_ablocks, n_slots = gridDim.x / n_ablocks;
+  const ABlock ab = blocks[a];
+  const QFrame fr = frames[ab.frame];
+  const int nq_blk = min(kQPerCta, fr.nq - ab.q0);            // queries of this block (> 0 by construction)
+  const int m_tiles = (nq_blk + kQTile - 1) / kQTile;
+
+  if (threadIdx.x == 0) {
+    mbar_init(a_full, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&b_full[i], 128);
+      mbar_init(&b_empty[i], 1);
+      mbar_init(&acc_full[i], 1);
+      mbar_init(&acc_empty[i], 128);
+    }
+    mbar_fence_init();
+  }
+  if (warp == 8) tmem_alloc(tmem_slot, kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 8) {
+    // ===================== MMA issuer (one thread) =====================
+    if (lane == 0) {
+      mbar_expect_tx(a_full, (uint32_t)m_tiles * kATileBytes);
+      for (int m = 0; m < m_tiles; ++m) bulk_g2s(sA + m * kATileBytes, ab.img + (size_t)m * kATileBytes, kATileBytes, a_full);
+      mbar_wait_guard(a_full, 0);
+      uint32_t par_bfull[2] = {0, 0}, par_accempty[2] = {1, 1}, n_commit[2] = {0, 0};
+      int bb = 0, as = 0;
+      const uint32_t sA_addr = smem_u32(sA), sB_addr = smem_u32(sB);
+      for (int k = k0 + slot; k < k0 + kc; k += n_slots) {
+        const KfEntry kf = kfs[k];
+        if (!kf_eligible(fr.cur_id, kf.frame_id, kb) || kf.n <= 0) continue;
+        for (int row0 = 0; row0 < kf.n; row0 += kTN) {
+          const int cnt = min(kTN, kf.n - row0);
+          const uint32_t idesc = instr_desc((cnt + 15) & ~15);
+          mbar_wait_guard(&b_full[bb], par_bfull[bb]);
+          par_bfull[bb] ^= 1;
+          tc_fence_after();
+          for (int m = 0; m < m_tiles; ++m) {
+            mbar_wait_guard(&acc_empty[as], par_accempty[as]);
+            par_accempty[as] ^= 1;
+            tc_fence_after();
+            const uint32_t d = tmem_base + (uint32_t)as * kAccStride;
+#pragma unroll
+            for (int s = 0; s < 8; ++s) {  // K = 256 = 2 K-blocks x 4 steps of 32 bytes
+              const uint32_t aoff = (uint32_t)m * kATileBytes + (uint32_t)(s >> 2) * (kQTile * 128) + (uint32_t)(s & 3) * 32;
+              const uint32_t boff = (uint32_t)bb * kBTileBytes + (uint32_t)(s >> 2) * (kTN * 128) + (uint32_t)(s & 3) * 32;
+              umma_i8(d, smem_desc(sA_addr + aoff), smem_desc(sB_addr + boff), idesc, s > 0 ? 1u : 0u);
+            }
+            umma_commit(&acc_full[as]);
+            as ^= 1;
+          }
+          umma_commit(&b_empty[bb]);  // every MMA that reads this B buffer has been issued
+          n_commit[bb] += 1;
+          bb ^= 1;
+        }
+      }
+      // do not leave while a commit may still arrive on this CTA's barriers
+      for (int i = 0; i < 2; ++i)
+        if (n_commit[i]) mbar_wait_guard(&b_empty[i], (n_commit[i] - 1) & 1);
+    }
+  } else if (warp >= 4) {
+    // ===================== B expanders (128 threads) =====================
+    const int et = threadIdx.x - 128;
+    uint32_t par_bempty[2] = {1, 1};
+    int bb = 0;
+    for (int k = k0 + slot; k < k0 + kc; k += n_slots) {
+      const KfEntry kf = kfs[k];
+      if (!kf_eligible(fr.cur_id, kf.frame_id, kb) || kf.n <= 0) continue;
+      const uint32_t* words = reinterpret_cast<const uint32_t*>(kf.rows);
+      for (int row0 = 0; row0 < kf.n; row0 += kTN) {
+        const int nwords = min(kTN, kf.n - row0) * 8;
+        uint32_t bits[kTN * 8 / 128];
+#pragma unroll
+        for (int i = 0; i < kTN * 8 / 128; ++i) {  // all loads in flight before the buffer is even free
+          const int idx = et + i * 128;
+          bits[i] = idx < nwords ? __ldg(words + (size_t)row0 * 8 + idx) : 0u;
+        }
+        mbar_wait_guard(&b_empty[bb], par_bempty[bb]);
+        par_bempty[bb] ^= 1;
+        uint8_t* tile = sB + bb * kBTileBytes;
+#pragma unroll
+        for (int i = 0; i < kTN * 8 / 128; ++i) {
+          const int idx = et + i * 128;
+          if (idx < nwords) {
+            uint32_t o0, o1;
+            tile_offsets(kTN, idx >> 3, idx & 7, o0, o1);
+            *reinterpret_cast<uint4*>(tile + o0) = expand_half(bits[i] & 0xffffu);
+            *reinterpret_cast<uint4*>(tile + o1) = expand_half(bits[i] >> 16);
+          }
+        }
+        fence_proxy_async();  // generic-proxy stores -> visible to the tensor core's async-proxy reads
+        mbar_arrive(&b_full[bb]);
+        bb ^= 1;
+      }
+    }
+  } else {
+    // ===================== epilogue (128 threads, warp w owns TMEM lanes 32w..32w+31) =====================
+    const int row = warp * 32 + lane;  // row inside an A tile
+    uint32_t par_accfull[2] = {0, 0};
+    int as = 0;
+    const int unit = (int)kb.key_unit;
+    for (int k = k0 + slot; k < k0 + kc; k += n_slots) {
+      const KfEntry kf = kfs[k];
+      if (!kf_eligible(fr.cur_id, kf.frame_id, kb) || kf.n <= 0) continue;
+      int best[kQTilesPerCta];
+#pragma unroll
+      for (int m = 0; m < kQTilesPerCta; ++m) best[m] = (int)0x80000000;
+      for (int row0 = 0; row0 < kf.n; row0 += kTN) {
+        const int cnt = min(kTN, kf.n - row0);
+#pragma unroll
+        for (int m = 0; m < kQTilesPerCta; ++m) {
+          if (m < m_tiles) {
+            mbar_wait_guard(&acc_full[as], par_accfull[as]);
+            par_accfull[as] ^= 1;
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)as * kAccStride;
+            const int tkey = fold_accumulator(taddr, cnt, unit);
+            tc_fence_before();
+            mbar_arrive(&acc_empty[as]);  // accumulator stage drained
+            as ^= 1;
+            best[m] = max(best[m], tkey + ((int)kKeyRowMask - row0));
+          }
+        }
+      }
+      // dot -> distance, store dist << 20 | row for finalize_kernel
+      uint32_t* dst = scratch + ((size_t)ab.frame * kc + (k - k0)) * scratch_stride + ab.q0;
+#pragma unroll
+      for (int m = 0; m < kQTilesPerCta; ++m) {
+        const int q = m * kQTile + row;
+        if (q < nq_blk) {
+          const int dot = best[m] >> kKeyShift;  // arithmetic shift: key = dot * 2^20 + (2^20 - 1 - row)
+          const uint32_t r = kKeyRowMask - ((uint32_t)best[m] & kKeyRowMask);
+          dst[q] = ((uint32_t)((256 - dot) >> 1) << kKeyShift) | r;
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 8) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+}  // namespace tc
+}  // namespace lc
