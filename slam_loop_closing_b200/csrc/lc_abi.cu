@@ -9,6 +9,7 @@
 #include <algorithm>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <limits>
 #include <new>
@@ -127,7 +128,8 @@ int ensure_pin_down(lc_ctx* c, size_t bytes) {
 }
 
 Knobs knobs_of(const lc_config& g) {
-  return Knobs{g.min_loop_gap, g.gap_strict, g.filter_floor, g.filter_strict, g.min_init, 1u << kKeyShift};
+  static const int dbg = getenv("LC_TC_DEBUG") ? atoi(getenv("LC_TC_DEBUG")) : 0;
+  return Knobs{g.min_loop_gap, g.gap_strict, g.filter_floor, g.filter_strict, g.min_init, 1u << kKeyShift, dbg};
 }
 
 int mode_of(const lc_config& g) { return g.kernel == LC_KERNEL_POPC ? MODE_POPC : MODE_CSA; }  // the tensor path falls back to CSA for tiny problems
@@ -335,6 +337,7 @@ int run_match(lc_ctx* c, cudaStream_t st, const KfEntry* d_kfs, int n_kf, int ma
       c->timing.kernel_launches += 1;
       for (int k0 = 0; k0 < n_kf; k0 += (int)kc_max) {
         const int kc = (int)std::min<long long>(kc_max, n_kf - k0);
+        LC_CUDA(c, cudaMemsetAsync(c->d_scratch.p, 0xff, (size_t)kc * n_frames * stride * 4, st));
         tc::tensor_match_kernel<<<n_ab * std::min(n_slots, kc), tc::kThreads, tc::kSmemAlloc, st>>>(
             d_kfs, k0, kc, d_frames, (const tc::ABlock*)c->d_ablocks.p, n_ab, (uint32_t*)c->d_scratch.p, stride, kb);
         LC_CUDA(c, cudaGetLastError());

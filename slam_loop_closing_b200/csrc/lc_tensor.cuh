@@ -12,10 +12,13 @@
 //     into the exact 128B-swizzled K-major smem image (4 tiles x 32 KiB) and pulled in with 1-D TMA bulk
 //     copies.  Streaming A per tile would need ~32 B/clk/SM of L2 bandwidth chip-wide.
 //   * B (keyframe rows) is expanded IN the kernel from the 32-byte packed rows (so the store stays
-//     32 B/row in HBM): 4 expander warps turn 192 rows into a 48 KiB swizzled tile, double buffered.
-//   * D lives in TMEM (2 stages x 192 columns); 4 epilogue warps read their lane quadrant with
-//     tcgen05.ld.32x32b and fold 192 columns into one key per row: 1 IMAD + 1/2 VIMNMX3 per pair.
-//   * one elected thread issues the MMAs; mbarriers + tcgen05.commit connect the three roles.
+//     32 B/row in HBM): 4 expander warps turn 128 rows into a 32 KiB swizzled tile, 3 stages.
+//   * D lives in TMEM (4 stages x 128 columns = all of it); 8 epilogue warps (lane quadrant x column half) read
+//     it with tcgen05.ld.32x32b and fold 64 columns into one key per row: 1 IMAD + 1/2 VIMNMX3 per pair.  Four
+//     stages matter: tcgen05.mma issue back-pressures the issuing thread (the queue is shallow), so any wait of the
+//     MMA warp on a not-yet-drained accumulator is a bubble in the tensor pipe.
+//   * two issuer warps (one elected lane each, alternating A tiles) issue the MMAs; mbarriers + tcgen05.commit
+//     connect the three roles.
 // Output: one u32 key (dist << 20 | row) per (frame, keyframe, query) into the scratch that
 // finalize_kernel reduces - the same contract as split_kernel.
 #pragma once
@@ -27,15 +30,24 @@ namespace tc {
 constexpr int kQTile = 128;                 // UMMA M
 constexpr int kQTilesPerCta = 4;            // resident A tiles
 constexpr int kQPerCta = kQTile * kQTilesPerCta;
-constexpr int kTN = 192;                    // train rows per B tile (UMMA N, multiple of 16)
+constexpr int kTN = 128;                    // train rows per B tile (UMMA N)
+constexpr int kBStages = 3;                 // expanded B tiles in flight
+constexpr int kAccStages = 4;               // TMEM accumulator stages: 4 x 128 columns = all 512
 constexpr int kATileBytes = kQTile * 256;   // 32 KiB: 2 K-blocks x 128 rows x 128 B
-constexpr int kBTileBytes = kTN * 256;      // 48 KiB
+constexpr int kBTileBytes = kTN * 256;      // 32 KiB
 constexpr int kABytes = kQTilesPerCta * kATileBytes;
-constexpr int kSmemBytes = kABytes + 2 * kBTileBytes + 256;  // + barriers
-constexpr int kSmemAlloc = kSmemBytes + 1024;                // manual 1024-B alignment
-constexpr int kThreads = 288;               // warps 0-3 epilogue, 4-7 expanders, 8 MMA issuer
-constexpr int kAccStride = 256;             // TMEM columns between the two accumulator stages
+constexpr int kBarBytes = 256;
+constexpr int kSmemAlloc = kABytes + kBStages * kBTileBytes + kBarBytes;  // 229,632 B of the 232,448 B limit
+constexpr int kEpiWarps = 8;                // warp w: TMEM lane quadrant w % 4, column half w / 4
+constexpr int kExpWarps = 4;
+constexpr int kMmaWarp = kEpiWarps + kExpWarps;
+constexpr int kMmaWarps = 2;                // issuer w handles A tiles m = w, w + 2 (tcgen05.mma costs its issuing
+                                            // thread ~48 clk, so one thread cannot feed 64-clk N=128 MMAs plus barriers)
+constexpr int kThreads = (kMmaWarp + kMmaWarps) * 32;  // 448: warps 0-7 epilogue, 8-11 expanders, 12-13 MMA issuers
+constexpr int kColsPerEpiWarp = kTN / 2;    // 64
+constexpr int kAccStride = kTN;             // TMEM columns per accumulator stage
 constexpr int kTmemCols = 512;
+constexpr int kWordsPerExpThread = kTN * 8 / (kExpWarps * 32);  // 8
 
 struct ABlock {          // one resident query block: 512 queries of one frame
   const uint8_t* img;    // expanded smem image (kABytes), written by expand_queries_kernel
@@ -96,6 +108,11 @@ __device__ __forceinline__ void mbar_wait_guard(uint64_t* bar, uint32_t parity) 
   for (uint32_t spins = 0; !mbar_try(bar, parity); ++spins)
     if (spins > (1u << 24)) __trap();
 }
+__device__ __forceinline__ bool elect_one() {  // one lane of the (converged) warp
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
@@ -146,29 +163,92 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, int (&v)[32]) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
-// Fold this thread's row of one accumulator stage (cnt valid columns) into a key
-//   max_c (dot[c] * 2^20 - c):  the maximum picks the largest dot product, then the lowest column.
-// Not inlined: the body is ~600 instructions and is called from four unrolled sites.
-__device__ __noinline__ int fold_accumulator(uint32_t taddr, int cnt, int unit) {
-  int tkey = (int)0x80000000;
+// Fold this thread's row of columns [c0, c0 + 64) of one accumulator stage (cnt valid columns in the stage)
+// into  max_c (dot[c] * 2^20 - c):  the maximum picks the largest dot product, then the lowest column.
+// Both TMEM loads are issued back to back and waited for once; four independent running maxima keep the
+// VIMNMX3 dependency chains short.
+__device__ __forceinline__ int fold_accumulator(uint32_t taddr, int c0, int cnt, int unit) {
+  constexpr int NEG = (int)0x80000000;
+  if (c0 >= cnt) return NEG;
+  int v[kColsPerEpiWarp];
+  int (&v0)[32] = *reinterpret_cast<int (*)[32]>(&v[0]);
+  int (&v1)[32] = *reinterpret_cast<int (*)[32]>(&v[32]);
+  tmem_ld32(taddr + c0, v0);
+  if (c0 + 32 < cnt) tmem_ld32(taddr + c0 + 32, v1);
+  tmem_ld_wait();
+  int k0 = NEG, k1 = NEG, k2 = NEG, k3 = NEG;
+  if (c0 + kColsPerEpiWarp <= cnt) {
 #pragma unroll
-  for (int c = 0; c < kTN / 32; ++c) {
-    if (c * 32 < cnt) {
-      int v[32];
-      tmem_ld32(taddr + c * 32, v);
-      tmem_ld_wait();
-      if ((c + 1) * 32 <= cnt) {
+    for (int j = 0; j < kColsPerEpiWarp; j += 8) {
+      k0 = max(k0, max(v[j + 0] * unit - (j + 0), v[j + 1] * unit - (j + 1)));
+      k1 = max(k1, max(v[j + 2] * unit - (j + 2), v[j + 3] * unit - (j + 3)));
+      k2 = max(k2, max(v[j + 4] * unit - (j + 4), v[j + 5] * unit - (j + 5)));
+      k3 = max(k3, max(v[j + 6] * unit - (j + 6), v[j + 7] * unit - (j + 7)));
+    }
+  } else {
+    const int lim = cnt - c0;
 #pragma unroll
-        for (int j = 0; j < 32; j += 2)
-          tkey = max(tkey, max(v[j] * unit - (c * 32 + j), v[j + 1] * unit - (c * 32 + j + 1)));
-      } else {
+    for (int j = 0; j < kColsPerEpiWarp; ++j)
+      if (j < lim) k0 = max(k0, v[j] * unit - j);
+  }
+  return max(max(k0, k1), max(k2, k3)) - c0;
+}
+
+// ---------------------------------------------------------------- MMA issuer warp
+// The whole warp runs the (uniform) control flow so descriptors live in uniform registers; one elected lane issues
+// tcgen05.mma / tcgen05.commit.  (Issuing from inside an `if (lane == 0)` region makes ptxas wrap every MMA in an
+// ELECT/R2UR.BROADCAST waterfall: ~100 clk per instruction.)  Accumulator stage == A tile index m, so every stage
+// is used exactly once per B tile and one parity bit serves all of them.
+template <int WI>
+__device__ __forceinline__ void mma_issuer(const KfEntry* __restrict__ kfs, int k0, int kc, int slot, int n_slots, const QFrame& fr,
+                                           const Knobs& kb, int m_tiles, uint32_t tmem_base, uint32_t sA_addr, uint32_t sB_addr,
+                                           uint64_t* a_full, uint64_t* b_full, uint64_t* b_empty, uint64_t* acc_full,
+                                           uint64_t* acc_empty) {
+  const bool leader = elect_one();
+  mbar_wait_guard(a_full, 0);
+  uint32_t par_bfull = 0, par_acc = 1, n_btiles = 0;
+  int bb = 0;
+  const uint64_t adesc0 = smem_desc(sA_addr), bdesc0 = smem_desc(sB_addr);
+  for (int k = k0 + slot; k < k0 + kc; k += n_slots) {
+    const KfEntry kf = kfs[k];
+    if (!kf_eligible(fr.cur_id, kf.frame_id, kb) || kf.n <= 0) continue;
+    for (int row0 = 0; row0 < kf.n; row0 += kTN) {
+      const int cnt = min(kTN, kf.n - row0);
+      const uint32_t idesc = instr_desc((cnt + 15) & ~15);
+      const uint64_t bdesc = bdesc0 + (uint64_t)((bb * kBTileBytes) >> 4);
+      mbar_wait_guard(&b_full[bb], (par_bfull >> bb) & 1);
+      par_bfull ^= 1u << bb;
+      tc_fence_after();
 #pragma unroll
-        for (int j = 0; j < 32; ++j)
-          if (c * 32 + j < cnt) tkey = max(tkey, v[j] * unit - (c * 32 + j));
+      for (int m = WI; m < kQTilesPerCta; m += kMmaWarps) {
+        if (m < m_tiles) {
+          mbar_wait_guard(&acc_empty[m], par_acc);
+          tc_fence_after();
+          if (leader) {
+            const uint32_t d = tmem_base + (uint32_t)m * kAccStride;
+            const uint64_t adesc = adesc0 + (uint64_t)((m * kATileBytes) >> 4);
+#pragma unroll
+            for (int s = 0; s < 8; ++s) {  // K = 256 = 2 K-blocks x 4 steps of 32 bytes
+              const uint32_t ka = (uint32_t)(s >> 2) * (kQTile * 128) + (uint32_t)(s & 3) * 32;
+              const uint32_t kbo = (uint32_t)(s >> 2) * (kTN * 128) + (uint32_t)(s & 3) * 32;
+              umma_i8(d, adesc + (ka >> 4), bdesc + (kbo >> 4), idesc, s > 0 ? 1u : 0u);
+            }
+            umma_commit(&acc_full[m]);
+          }
+        }
       }
+      if (leader) umma_commit(&b_empty[bb]);  // arrives when this warp's MMAs reading the B stage have completed
+      par_acc ^= 1;
+      n_btiles += 1;
+      bb = bb + 1 == kBStages ? 0 : bb + 1;
     }
   }
-  return tkey;
+  // do not leave while a commit may still arrive on this CTA's barriers
+#pragma unroll
+  for (int i = 0; i < kBStages; ++i) {
+    const uint32_t n_i = (n_btiles + (kBStages - 1 - i)) / kBStages;  // phases completed on b_empty[i]
+    if (n_i) mbar_wait_guard(&b_empty[i], (n_i - 1) & 1);
+  }
 }
 
 // ---------------------------------------------------------------- the kernel
@@ -178,17 +258,16 @@ __global__ void __launch_bounds__(kThreads, 1)
     tensor_match_kernel(const KfEntry* __restrict__ kfs, int k0, int kc, const QFrame* __restrict__ frames,
                         const ABlock* __restrict__ blocks, int n_ablocks, uint32_t* __restrict__ scratch, int scratch_stride,
                         Knobs kb) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  extern __shared__ __align__(1024) uint8_t smem[];  // SWIZZLE_128B operands need 1024-byte alignment
   uint8_t* sA = smem;
   uint8_t* sB = smem + kABytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kABytes + 2 * kBTileBytes);
-  uint64_t* a_full = bars;          // 1 arrival + tx bytes
-  uint64_t* b_full = bars + 1;      // [2] 128 expander arrivals
-  uint64_t* b_empty = bars + 3;     // [2] 1 commit
-  uint64_t* acc_full = bars + 5;    // [2] 1 commit
-  uint64_t* acc_empty = bars + 7;   // [2] 128 epilogue arrivals
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kABytes + kBStages * kBTileBytes);
+  uint64_t* a_full = bars;                          // 1 arrival + tx bytes
+  uint64_t* b_full = bars + 1;                      // [kBStages] one arrival per expander thread
+  uint64_t* b_empty = b_full + kBStages;            // [kBStages] one commit per MMA issuer warp
+  uint64_t* acc_full = b_empty + kBStages;          // [kAccStages] 1 commit
+  uint64_t* acc_empty = acc_full + kAccStages;      // [kAccStages] one arrival per epilogue thread
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + kAccStages);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int a = blockIdx.x % n_ablocks, slot = blockIdx.x / n_ablocks, n_slots = gridDim.x / n_ablocks;
@@ -198,66 +277,39 @@ __global__ void __launch_bounds__(kThreads, 1)
   const int m_tiles = (nq_blk + kQTile - 1) / kQTile;
 
   if (threadIdx.x == 0) {
+    if (smem_u32(smem) & 1023u) __trap();
     mbar_init(a_full, 1);
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(&b_full[i], 128);
-      mbar_init(&b_empty[i], 1);
+    for (int i = 0; i < kBStages; ++i) {
+      mbar_init(&b_full[i], kExpWarps * 32);
+      mbar_init(&b_empty[i], kMmaWarps);
+    }
+    for (int i = 0; i < kAccStages; ++i) {
       mbar_init(&acc_full[i], 1);
-      mbar_init(&acc_empty[i], 128);
+      mbar_init(&acc_empty[i], kEpiWarps * 32);
     }
     mbar_fence_init();
   }
-  if (warp == 8) tmem_alloc(tmem_slot, kTmemCols);
+  if (warp == kMmaWarp) tmem_alloc(tmem_slot, kTmemCols);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 8) {
-    // ===================== MMA issuer (one thread) =====================
-    if (lane == 0) {
+  if (warp >= kMmaWarp) {
+    // ===================== MMA issuers (2 warps) =====================
+    if (warp == kMmaWarp && lane == 0) {
       mbar_expect_tx(a_full, (uint32_t)m_tiles * kATileBytes);
       for (int m = 0; m < m_tiles; ++m) bulk_g2s(sA + m * kATileBytes, ab.img + (size_t)m * kATileBytes, kATileBytes, a_full);
-      mbar_wait_guard(a_full, 0);
-      uint32_t par_bfull[2] = {0, 0}, par_accempty[2] = {1, 1}, n_commit[2] = {0, 0};
-      int bb = 0, as = 0;
-      const uint32_t sA_addr = smem_u32(sA), sB_addr = smem_u32(sB);
-      for (int k = k0 + slot; k < k0 + kc; k += n_slots) {
-        const KfEntry kf = kfs[k];
-        if (!kf_eligible(fr.cur_id, kf.frame_id, kb) || kf.n <= 0) continue;
-        for (int row0 = 0; row0 < kf.n; row0 += kTN) {
-          const int cnt = min(kTN, kf.n - row0);
-          const uint32_t idesc = instr_desc((cnt + 15) & ~15);
-          mbar_wait_guard(&b_full[bb], par_bfull[bb]);
-          par_bfull[bb] ^= 1;
-          tc_fence_after();
-          for (int m = 0; m < m_tiles; ++m) {
-            mbar_wait_guard(&acc_empty[as], par_accempty[as]);
-            par_accempty[as] ^= 1;
-            tc_fence_after();
-            const uint32_t d = tmem_base + (uint32_t)as * kAccStride;
-#pragma unroll
-            for (int s = 0; s < 8; ++s) {  // K = 256 = 2 K-blocks x 4 steps of 32 bytes
-              const uint32_t aoff = (uint32_t)m * kATileBytes + (uint32_t)(s >> 2) * (kQTile * 128) + (uint32_t)(s & 3) * 32;
-              const uint32_t boff = (uint32_t)bb * kBTileBytes + (uint32_t)(s >> 2) * (kTN * 128) + (uint32_t)(s & 3) * 32;
-              umma_i8(d, smem_desc(sA_addr + aoff), smem_desc(sB_addr + boff), idesc, s > 0 ? 1u : 0u);
-            }
-            umma_commit(&acc_full[as]);
-            as ^= 1;
-          }
-          umma_commit(&b_empty[bb]);  // every MMA that reads this B buffer has been issued
-          n_commit[bb] += 1;
-          bb ^= 1;
-        }
-      }
-      // do not leave while a commit may still arrive on this CTA's barriers
-      for (int i = 0; i < 2; ++i)
-        if (n_commit[i]) mbar_wait_guard(&b_empty[i], (n_commit[i] - 1) & 1);
     }
-  } else if (warp >= 4) {
+    __syncwarp();
+    if (warp == kMmaWarp)
+      mma_issuer<0>(kfs, k0, kc, slot, n_slots, fr, kb, m_tiles, tmem_base, smem_u32(sA), smem_u32(sB), a_full, b_full, b_empty, acc_full, acc_empty);
+    else
+      mma_issuer<1>(kfs, k0, kc, slot, n_slots, fr, kb, m_tiles, tmem_base, smem_u32(sA), smem_u32(sB), a_full, b_full, b_empty, acc_full, acc_empty);
+  } else if (warp >= kEpiWarps) {
     // ===================== B expanders (128 threads) =====================
-    const int et = threadIdx.x - 128;
-    uint32_t par_bempty[2] = {1, 1};
+    const int et = threadIdx.x - kEpiWarps * 32;
+    uint32_t par_bempty = (1u << kBStages) - 1;
     int bb = 0;
     for (int k = k0 + slot; k < k0 + kc; k += n_slots) {
       const KfEntry kf = kfs[k];
@@ -265,18 +317,18 @@ __global__ void __launch_bounds__(kThreads, 1)
       const uint32_t* words = reinterpret_cast<const uint32_t*>(kf.rows);
       for (int row0 = 0; row0 < kf.n; row0 += kTN) {
         const int nwords = min(kTN, kf.n - row0) * 8;
-        uint32_t bits[kTN * 8 / 128];
+        uint32_t bits[kWordsPerExpThread];
 #pragma unroll
-        for (int i = 0; i < kTN * 8 / 128; ++i) {  // all loads in flight before the buffer is even free
-          const int idx = et + i * 128;
+        for (int i = 0; i < kWordsPerExpThread; ++i) {  // all loads in flight before the buffer is even free
+          const int idx = et + i * (kExpWarps * 32);
           bits[i] = idx < nwords ? __ldg(words + (size_t)row0 * 8 + idx) : 0u;
         }
-        mbar_wait_guard(&b_empty[bb], par_bempty[bb]);
-        par_bempty[bb] ^= 1;
+        mbar_wait_guard(&b_empty[bb], (par_bempty >> bb) & 1);
+        par_bempty ^= 1u << bb;
         uint8_t* tile = sB + bb * kBTileBytes;
 #pragma unroll
-        for (int i = 0; i < kTN * 8 / 128; ++i) {
-          const int idx = et + i * 128;
+        for (int i = 0; i < kWordsPerExpThread; ++i) {
+          const int idx = et + i * (kExpWarps * 32);
           if (idx < nwords) {
             uint32_t o0, o1;
             tile_offsets(kTN, idx >> 3, idx & 7, o0, o1);
@@ -286,14 +338,15 @@ __global__ void __launch_bounds__(kThreads, 1)
         }
         fence_proxy_async();  // generic-proxy stores -> visible to the tensor core's async-proxy reads
         mbar_arrive(&b_full[bb]);
-        bb ^= 1;
+        bb = bb + 1 == kBStages ? 0 : bb + 1;
       }
     }
   } else {
-    // ===================== epilogue (128 threads, warp w owns TMEM lanes 32w..32w+31) =====================
-    const int row = warp * 32 + lane;  // row inside an A tile
-    uint32_t par_accfull[2] = {0, 0};
-    int as = 0;
+    // ===================== epilogue (256 threads: warp w owns TMEM lanes 32(w%4).. and columns 96(w/4)..) ====
+    const int quad = warp & 3, half = warp >> 2;
+    const int row = quad * 32 + lane;  // row inside an A tile
+    const int c0 = half * kColsPerEpiWarp;
+    uint32_t par_accfull = 0;  // accumulator stage == m: every stage completes once per B tile
     const int unit = (int)kb.key_unit;
     for (int k = k0 + slot; k < k0 + kc; k += n_slots) {
       const KfEntry kf = kfs[k];
@@ -303,37 +356,34 @@ __global__ void __launch_bounds__(kThreads, 1)
       for (int m = 0; m < kQTilesPerCta; ++m) best[m] = (int)0x80000000;
       for (int row0 = 0; row0 < kf.n; row0 += kTN) {
         const int cnt = min(kTN, kf.n - row0);
-#pragma unroll
-        for (int m = 0; m < kQTilesPerCta; ++m) {
-          if (m < m_tiles) {
-            mbar_wait_guard(&acc_full[as], par_accfull[as]);
-            par_accfull[as] ^= 1;
-            tc_fence_after();
-            const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)as * kAccStride;
-            const int tkey = fold_accumulator(taddr, cnt, unit);
-            tc_fence_before();
-            mbar_arrive(&acc_empty[as]);  // accumulator stage drained
-            as ^= 1;
-            best[m] = max(best[m], tkey + ((int)kKeyRowMask - row0));
-          }
+#pragma unroll 1
+        for (int m = 0; m < m_tiles; ++m) {
+          mbar_wait_guard(&acc_full[m], par_accfull);
+          tc_fence_after();
+          const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)m * kAccStride;
+          int tkey = (int)0x80000000;
+          if (kb.debug == 0) tkey = fold_accumulator(taddr, c0, cnt, unit);  // the loads have completed when this returns
+          tc_fence_before();
+          mbar_arrive(&acc_empty[m]);  // accumulator stage drained by this thread
+          if (tkey != (int)0x80000000) best[m] = max(best[m], tkey + ((int)kKeyRowMask - row0));
         }
+        par_accfull ^= 1;
       }
-      // dot -> distance, store dist << 20 | row for finalize_kernel
+      // the two column halves of a row meet in scratch: dist << 20 | row, smaller is better
       uint32_t* dst = scratch + ((size_t)ab.frame * kc + (k - k0)) * scratch_stride + ab.q0;
-#pragma unroll
-      for (int m = 0; m < kQTilesPerCta; ++m) {
+      for (int m = 0; m < m_tiles; ++m) {
         const int q = m * kQTile + row;
-        if (q < nq_blk) {
+        if (q < nq_blk && best[m] != (int)0x80000000) {
           const int dot = best[m] >> kKeyShift;  // arithmetic shift: key = dot * 2^20 + (2^20 - 1 - row)
           const uint32_t r = kKeyRowMask - ((uint32_t)best[m] & kKeyRowMask);
-          dst[q] = ((uint32_t)((256 - dot) >> 1) << kKeyShift) | r;
+          atomicMin(dst + q, ((uint32_t)((256 - dot) >> 1) << kKeyShift) | r);
         }
       }
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 8) {
+  if (warp == kMmaWarp) {
     tc_fence_after();
     tmem_dealloc(tmem_base, kTmemCols);
   }
