@@ -47,7 +47,8 @@ typedef enum lc_status {
 } lc_status;
 
 typedef enum lc_kernel {
-  LC_KERNEL_AUTO = 0, /* library default (the measured-fastest bit-exact integer path) */
+  LC_KERNEL_AUTO = 0, /* library default: the measured-fastest bit-exact path (tensor cores when the problem fills
+                         the GPU, else the carry-save integer kernels) */
   LC_KERNEL_POPC = 1, /* 8 x (XOR, POPC) per pair: the naive integer-popc formulation */
   LC_KERNEL_CSA = 2,  /* carry-save adder tree: 16 LOP3 + 4 POPC per pair, same result */
   LC_KERNEL_TENSOR = 3 /* tcgen05.mma kind::i8 on +1/-1 expanded bits (dot = 256 - 2*hamming) + arg-max epilogue, same

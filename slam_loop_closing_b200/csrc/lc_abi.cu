@@ -9,7 +9,6 @@
 #include <algorithm>
 #include <cstdarg>
 #include <cstdio>
-#include <cstdlib>
 #include <cstring>
 #include <limits>
 #include <new>
@@ -128,8 +127,7 @@ int ensure_pin_down(lc_ctx* c, size_t bytes) {
 }
 
 Knobs knobs_of(const lc_config& g) {
-  static const int dbg = getenv("LC_TC_DEBUG") ? atoi(getenv("LC_TC_DEBUG")) : 0;
-  return Knobs{g.min_loop_gap, g.gap_strict, g.filter_floor, g.filter_strict, g.min_init, 1u << kKeyShift, dbg};
+  return Knobs{g.min_loop_gap, g.gap_strict, g.filter_floor, g.filter_strict, g.min_init, 1u << kKeyShift};
 }
 
 int mode_of(const lc_config& g) { return g.kernel == LC_KERNEL_POPC ? MODE_POPC : MODE_CSA; }  // the tensor path falls back to CSA for tiny problems
@@ -289,8 +287,68 @@ int run_match(lc_ctx* c, cudaStream_t st, const KfEntry* d_kfs, int n_kf, int ma
   for (int f = 0; f < n_frames; ++f) max_nq = std::max(max_nq, h_frames[f].nq);
   const int mode = mode_of(c->cfg);
 
+  // ---- tensor cores: int8 GEMM + arg-max (lc_tensor.cuh) when there is a machine's worth of work
+  const bool want_tensor = c->cfg.kernel == LC_KERNEL_TENSOR || c->cfg.kernel == LC_KERNEL_AUTO;
+  if (want_tensor && !force_split && max_nq > 0 && max_rows > 0) {
+    std::vector<tc::ABlock> blocks;
+    std::vector<int> tiles;
+    long long total_tiles = 0;
+    for (int f = 0; f < n_frames; ++f)
+      for (int q0 = 0; q0 < h_frames[f].nq; q0 += tc::kQPerCta) {
+        blocks.push_back(tc::ABlock{nullptr, f, q0});
+        tiles.push_back((std::min(tc::kQPerCta, h_frames[f].nq - q0) + tc::kQTile - 1) / tc::kQTile);
+        total_tiles += tiles.back();
+      }
+    const int n_ab = (int)blocks.size();
+    if ((long long)n_ab * n_kf >= c->num_sms) {
+      // CTAs per query block: proportional to its number of 128-row tiles (a ragged last block gets fewer), about one
+      // CTA per SM in total; with more query blocks than SMs, enough CTAs for >= 4 waves
+      std::vector<tc::CtaWork> work;
+      for (int i = 0; i < n_ab; ++i) {
+        long long ns = n_ab <= c->num_sms ? std::max<long long>(1, ((long long)c->num_sms * tiles[i]) / total_tiles)
+                                          : (4ll * c->num_sms + n_ab - 1) / n_ab;
+        ns = std::min<long long>(ns, n_kf);
+        for (int s = 0; s < (int)ns; ++s) work.push_back(tc::CtaWork{i, s, (int)ns});
+      }
+      LC_TRY(ensure(c, c->d_qimg, (size_t)n_ab * tc::kABytes));
+      LC_TRY(ensure(c, c->d_ablocks, (size_t)n_ab * sizeof(tc::ABlock) + work.size() * sizeof(tc::CtaWork)));
+      for (int i = 0; i < n_ab; ++i) blocks[i].img = (const uint8_t*)c->d_qimg.p + (size_t)i * tc::kABytes;
+      tc::ABlock* d_blocks = (tc::ABlock*)c->d_ablocks.p;
+      tc::CtaWork* d_work = (tc::CtaWork*)(d_blocks + n_ab);
+      LC_CUDA(c, cudaMemcpyAsync(d_blocks, blocks.data(), (size_t)n_ab * sizeof(tc::ABlock), cudaMemcpyHostToDevice, st));
+      LC_CUDA(c, cudaMemcpyAsync(d_work, work.data(), work.size() * sizeof(tc::CtaWork), cudaMemcpyHostToDevice, st));
+      tc::expand_queries_kernel<<<n_ab, 256, 0, st>>>(d_blocks, d_frames, (uint8_t*)c->d_qimg.p);
+      LC_CUDA(c, cudaGetLastError());
+      static bool attr_set = false;
+      if (!attr_set) {
+        LC_CUDA(c, cudaFuncSetAttribute(tc::tensor_match_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kSmemAlloc));
+        attr_set = true;
+      }
+      const int stride = (max_nq + 3) & ~3;
+      long long kc_max = std::max<long long>(1, (long long)(kScratchBudgetBytes / ((size_t)stride * 4)) / n_frames);
+      kc_max = std::min<long long>(kc_max, n_kf);
+      LC_TRY(ensure(c, c->d_scratch, (size_t)kc_max * n_frames * stride * 4));
+      c->launches += 1;
+      c->timing.kernel_launches += 1;
+      for (int k0 = 0; k0 < n_kf; k0 += (int)kc_max) {
+        const int kc = (int)std::min<long long>(kc_max, n_kf - k0);
+        LC_CUDA(c, cudaMemsetAsync(c->d_scratch.p, 0xff, (size_t)kc * n_frames * stride * 4, st));
+        tc::tensor_match_kernel<<<(unsigned)work.size(), tc::kThreads, tc::kSmemAlloc, st>>>(
+            d_kfs, k0, kc, d_frames, d_blocks, d_work, (uint32_t*)c->d_scratch.p, stride, kb);
+        LC_CUDA(c, cudaGetLastError());
+        finalize_kernel<<<kc * n_frames, 256, 0, st>>>(d_kfs, n_kf, k0, kc, d_frames, (const uint32_t*)c->d_scratch.p, stride,
+                                                       d_results, po.train_idx, po.dist, po.good, po.summary, kb);
+        LC_CUDA(c, cudaGetLastError());
+        c->launches += 2;
+        c->timing.kernel_launches += 2;
+      }
+      c->timing.path = 3;
+      return LC_OK;
+    }
+  }
+
   // ---- whole-keyframe scan: enough items to fill every CTA slot many times over
-  if (!force_split && c->cfg.kernel != LC_KERNEL_TENSOR && max_nq <= kFusedMaxNq && max_nq > 0) {
+  if (!force_split && max_nq <= kFusedMaxNq && max_nq > 0) {
     const Shape sh = scan_shape(max_nq);
     const int occ = mode == MODE_POPC ? scan_occupancy<MODE_POPC>(sh.rq, sh.threads) : scan_occupancy<MODE_CSA>(sh.rq, sh.threads);
     const long long slots = (long long)c->num_sms * occ;
@@ -305,49 +363,6 @@ int run_match(lc_ctx* c, cudaStream_t st, const KfEntry* d_kfs, int n_kf, int ma
       c->launches += 1;
       c->timing.kernel_launches += 1;
       c->timing.path = 1;
-      return LC_OK;
-    }
-  }
-
-  // ---- tensor cores: int8 GEMM + arg-max (lc_tensor.cuh) when there is a machine's worth of work
-  if (c->cfg.kernel == LC_KERNEL_TENSOR && !force_split && max_nq > 0 && max_rows > 0) {
-    std::vector<tc::ABlock> blocks;
-    for (int f = 0; f < n_frames; ++f)
-      for (int q0 = 0; q0 < h_frames[f].nq; q0 += tc::kQPerCta)
-        blocks.push_back(tc::ABlock{nullptr, f, q0});
-    const int n_ab = (int)blocks.size();
-    if ((long long)n_ab * n_kf >= c->num_sms) {
-      LC_TRY(ensure(c, c->d_qimg, (size_t)n_ab * tc::kABytes));
-      LC_TRY(ensure(c, c->d_ablocks, (size_t)n_ab * sizeof(tc::ABlock)));
-      for (int i = 0; i < n_ab; ++i) blocks[i].img = (const uint8_t*)c->d_qimg.p + (size_t)i * tc::kABytes;
-      LC_CUDA(c, cudaMemcpyAsync(c->d_ablocks.p, blocks.data(), (size_t)n_ab * sizeof(tc::ABlock), cudaMemcpyHostToDevice, st));
-      tc::expand_queries_kernel<<<n_ab, 256, 0, st>>>((const tc::ABlock*)c->d_ablocks.p, d_frames, (uint8_t*)c->d_qimg.p);
-      LC_CUDA(c, cudaGetLastError());
-      static bool attr_set = false;
-      if (!attr_set) {
-        LC_CUDA(c, cudaFuncSetAttribute(tc::tensor_match_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kSmemAlloc));
-        attr_set = true;
-      }
-      const int stride = (max_nq + 3) & ~3;
-      long long kc_max = std::max<long long>(1, (long long)(kScratchBudgetBytes / ((size_t)stride * 4)) / n_frames);
-      kc_max = std::min<long long>(kc_max, n_kf);
-      LC_TRY(ensure(c, c->d_scratch, (size_t)kc_max * n_frames * stride * 4));
-      const int n_slots = std::max(1, c->num_sms / n_ab);
-      c->launches += 1;
-      c->timing.kernel_launches += 1;
-      for (int k0 = 0; k0 < n_kf; k0 += (int)kc_max) {
-        const int kc = (int)std::min<long long>(kc_max, n_kf - k0);
-        LC_CUDA(c, cudaMemsetAsync(c->d_scratch.p, 0xff, (size_t)kc * n_frames * stride * 4, st));
-        tc::tensor_match_kernel<<<n_ab * std::min(n_slots, kc), tc::kThreads, tc::kSmemAlloc, st>>>(
-            d_kfs, k0, kc, d_frames, (const tc::ABlock*)c->d_ablocks.p, n_ab, (uint32_t*)c->d_scratch.p, stride, kb);
-        LC_CUDA(c, cudaGetLastError());
-        finalize_kernel<<<kc * n_frames, 256, 0, st>>>(d_kfs, n_kf, k0, kc, d_frames, (const uint32_t*)c->d_scratch.p, stride,
-                                                       d_results, po.train_idx, po.dist, po.good, po.summary, kb);
-        LC_CUDA(c, cudaGetLastError());
-        c->launches += 2;
-        c->timing.kernel_launches += 2;
-      }
-      c->timing.path = 3;
       return LC_OK;
     }
   }

@@ -54,7 +54,6 @@ struct QFrame {  // one query frame
 struct Knobs {
   int32_t min_loop_gap, gap_strict, filter_floor, filter_strict, min_init;
   uint32_t key_unit;  // always 1 << kKeyShift; a runtime value on purpose (see ham_key)
-  int32_t debug;      // experiments only (LC_TC_DEBUG): 1 = tensor epilogue skips TMEM loads, 2 = loads but no math
 };
 
 // ---------------------------------------------------------------- PTX helpers (mbarrier + bulk copy)

@@ -1,9 +1,13 @@
 // lc_tensor.cuh - Hamming matching on the 5th-generation tensor cores (tcgen05.mma kind::i8, TMEM).
 //
-// Identity: with descriptor bits mapped to int8 +1 / -1,  dot(q, t) = 256 - 2 * hamming(q, t), so
-// argmin_j hamming == argmax_j dot and the whole match is a 128 x N x 256 int8 GEMM tile followed by a
-// row-wise arg-max.  All values are small integers, s32 accumulation is exact, the result is bit-identical
-// to the popc kernels (same key, same tie-break).
+// Identity: with query bits mapped to int8 +127 / -127 and train bits to +1 / -1,
+//     D[q][t] = 127 * (256 - 2 * hamming(q, t)),
+// so argmin_t hamming == argmax_t D and the whole match is a 128 x N x 256 int8 GEMM tile followed by a row-wise
+// max.  OpenCV's tie-break (lowest train row) is folded into the GEMM as well: a ninth K=32 step multiplies a
+// constant A (1 in k = 0) with a constant B (127 - column in k = 0), so D' = 127 * dot + (127 - column); dot is even,
+// consecutive dots are 254 apart and the tie term is < 128, hence max(D') = (max dot, then lowest column) and the
+// epilogue is ONE VIMNMX3 per two pairs - no per-pair multiply-add.  s32 accumulation is exact; the result is
+// bit-identical to the popc kernels (same key, same tie-break).
 //
 // Why this shape:
 //   * tcgen05.mma has no 1-bit kind and mma.sync b1 is emulated on sm_100a; kind::i8 at M=128 runs
@@ -36,8 +40,18 @@ constexpr int kAccStages = 4;               // TMEM accumulator stages: 4 x 128 
 constexpr int kATileBytes = kQTile * 256;   // 32 KiB: 2 K-blocks x 128 rows x 128 B
 constexpr int kBTileBytes = kTN * 256;      // 32 KiB
 constexpr int kABytes = kQTilesPerCta * kATileBytes;
+// Constant operands of the tie-break step (K-major, no swizzle: core matrix = 8 rows x 16 B).  Only k = 0 matters:
+//   A_tie: every row is [1, 0, ..., 0] -> ONE row group (2 K-chunks x 128 B) re-read for all 16 groups (SBO = 0);
+//   B_tie: row c holds 127 - c at k = 0 -> 16 groups x 128 B for K-chunk 0; K-chunk 1 aliases chunk 0 (LBO = 0), it is
+//          multiplied by A's zeros.
+constexpr int kTieABytes = 256;
+constexpr int kTieBBytes = 16 * 128;
 constexpr int kBarBytes = 256;
-constexpr int kSmemAlloc = kABytes + kBStages * kBTileBytes + kBarBytes;  // 229,632 B of the 232,448 B limit
+constexpr int kOffB = kABytes;
+constexpr int kOffTieA = kOffB + kBStages * kBTileBytes;
+constexpr int kOffTieB = kOffTieA + kTieABytes;
+constexpr int kOffBar = kOffTieB + kTieBBytes;
+constexpr int kSmemAlloc = kOffBar + kBarBytes;  // 231,936 B of the 232,448 B a CTA may have
 constexpr int kEpiWarps = 8;                // warp w: TMEM lane quadrant w % 4, column half w / 4
 constexpr int kExpWarps = 4;
 constexpr int kMmaWarp = kEpiWarps + kExpWarps;
@@ -54,17 +68,25 @@ struct ABlock {          // one resident query block: 512 queries of one frame
   int32_t frame;
   int32_t q0;
 };
+struct CtaWork {         // CTA -> (query block, its share of the keyframes): keyframes k0 + slot, + n_slots, ...
+  int32_t ablock;
+  int32_t slot;
+  int32_t n_slots;
+};
 
 // ---------------------------------------------------------------- bit -> int8 expansion
-// nibble (4 descriptor bits) -> 4 bytes, bit set -> -1 (0xFF), clear -> +1 (0x01)
+// nibble (4 descriptor bits) -> 4 bytes: bit clear -> +MAG, bit set -> -MAG  (MAG = 1 for trains, 127 for queries)
+template <int MAG>
 __device__ __forceinline__ uint32_t expand_nibble(uint32_t n) {
   const uint32_t s = (n * 0x00204081u) & 0x01010101u;  // bit i -> byte i (0/1); the partial products never overlap
-  return s * 0xFEu + 0x01010101u;                      // 0 -> 0x01, 1 -> 0xFF, no carries between bytes
+  constexpr uint32_t pos = (uint32_t)MAG & 0xffu, neg = (uint32_t)(-MAG) & 0xffu;
+  return s * (neg - pos) + pos * 0x01010101u;          // 0 -> pos, 1 -> neg, no carries between bytes
 }
 // 16 bits -> one 16-byte swizzle chunk
+template <int MAG>
 __device__ __forceinline__ uint4 expand_half(uint32_t h) {
-  return make_uint4(expand_nibble(h & 15u), expand_nibble((h >> 4) & 15u), expand_nibble((h >> 8) & 15u),
-                    expand_nibble((h >> 12) & 15u));
+  return make_uint4(expand_nibble<MAG>(h & 15u), expand_nibble<MAG>((h >> 4) & 15u), expand_nibble<MAG>((h >> 8) & 15u),
+                    expand_nibble<MAG>((h >> 12) & 15u));
 }
 // byte offset of (row r, 32-bit descriptor word w) inside a K-major SWIZZLE_128B tile of `rows` rows:
 // [K-block = w / 4][row][128 B], 16-byte chunk index XOR (row & 7)  (Swizzle<3,4,3>)
@@ -86,8 +108,8 @@ __global__ void expand_queries_kernel(const ABlock* __restrict__ blocks, const Q
     uint32_t o0, o1;
     tile_offsets(kQTile, ql & (kQTile - 1), w, o0, o1);
     uint8_t* tile = img + (size_t)(ql / kQTile) * kATileBytes;
-    *reinterpret_cast<uint4*>(tile + o0) = expand_half(bits & 0xffffu);
-    *reinterpret_cast<uint4*>(tile + o1) = expand_half(bits >> 16);
+    *reinterpret_cast<uint4*>(tile + o0) = expand_half<127>(bits & 0xffffu);
+    *reinterpret_cast<uint4*>(tile + o1) = expand_half<127>(bits >> 16);
   }
 }
 
@@ -144,6 +166,11 @@ __device__ __forceinline__ uint64_t smem_desc(uint32_t saddr) {
   return (uint64_t)((saddr & 0x3ffffu) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) |
          ((uint64_t)2 << 61);
 }
+// K-major, no swizzle ("interleaved"): core matrix = 8 rows x 16 B contiguous; next 16-byte K chunk at +lbo, next
+// 8-row group at +sbo
+__device__ __forceinline__ uint64_t smem_desc_noswz(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
+  return (uint64_t)((saddr & 0x3ffffu) >> 4) | ((uint64_t)(lbo >> 4) << 16) | ((uint64_t)(sbo >> 4) << 32) | ((uint64_t)1 << 46);
+}
 // s8 x s8 -> s32, both K-major, M = 128, N = n
 __device__ __forceinline__ uint32_t instr_desc(int n) {
   return (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(kQTile >> 4) << 24);
@@ -163,11 +190,10 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, int (&v)[32]) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
-// Fold this thread's row of columns [c0, c0 + 64) of one accumulator stage (cnt valid columns in the stage)
-// into  max_c (dot[c] * 2^20 - c):  the maximum picks the largest dot product, then the lowest column.
-// Both TMEM loads are issued back to back and waited for once; four independent running maxima keep the
-// VIMNMX3 dependency chains short.
-__device__ __forceinline__ int fold_accumulator(uint32_t taddr, int c0, int cnt, int unit) {
+// Fold this thread's row of columns [c0, c0 + 64) of one accumulator stage (cnt valid columns in the stage) into
+// max_c D'[c].  Both TMEM loads are issued back to back and waited for once; four independent running maxima keep
+// the VIMNMX3 dependency chains short.
+__device__ __forceinline__ int fold_accumulator(uint32_t taddr, int c0, int cnt) {
   constexpr int NEG = (int)0x80000000;
   if (c0 >= cnt) return NEG;
   int v[kColsPerEpiWarp];
@@ -180,18 +206,18 @@ __device__ __forceinline__ int fold_accumulator(uint32_t taddr, int c0, int cnt,
   if (c0 + kColsPerEpiWarp <= cnt) {
 #pragma unroll
     for (int j = 0; j < kColsPerEpiWarp; j += 8) {
-      k0 = max(k0, max(v[j + 0] * unit - (j + 0), v[j + 1] * unit - (j + 1)));
-      k1 = max(k1, max(v[j + 2] * unit - (j + 2), v[j + 3] * unit - (j + 3)));
-      k2 = max(k2, max(v[j + 4] * unit - (j + 4), v[j + 5] * unit - (j + 5)));
-      k3 = max(k3, max(v[j + 6] * unit - (j + 6), v[j + 7] * unit - (j + 7)));
+      k0 = max(k0, max(v[j + 0], v[j + 1]));
+      k1 = max(k1, max(v[j + 2], v[j + 3]));
+      k2 = max(k2, max(v[j + 4], v[j + 5]));
+      k3 = max(k3, max(v[j + 6], v[j + 7]));
     }
   } else {
     const int lim = cnt - c0;
 #pragma unroll
     for (int j = 0; j < kColsPerEpiWarp; ++j)
-      if (j < lim) k0 = max(k0, v[j] * unit - j);
+      if (j < lim) k0 = max(k0, v[j]);
   }
-  return max(max(k0, k1), max(k2, k3)) - c0;
+  return max(max(k0, k1), max(k2, k3));
 }
 
 // ---------------------------------------------------------------- MMA issuer warp
@@ -201,14 +227,15 @@ __device__ __forceinline__ int fold_accumulator(uint32_t taddr, int c0, int cnt,
 // is used exactly once per B tile and one parity bit serves all of them.
 template <int WI>
 __device__ __forceinline__ void mma_issuer(const KfEntry* __restrict__ kfs, int k0, int kc, int slot, int n_slots, const QFrame& fr,
-                                           const Knobs& kb, int m_tiles, uint32_t tmem_base, uint32_t sA_addr, uint32_t sB_addr,
+                                           const Knobs& kb, int m_tiles, uint32_t tmem_base, uint32_t sA_addr,
                                            uint64_t* a_full, uint64_t* b_full, uint64_t* b_empty, uint64_t* acc_full,
                                            uint64_t* acc_empty) {
   const bool leader = elect_one();
   mbar_wait_guard(a_full, 0);
   uint32_t par_bfull = 0, par_acc = 1, n_btiles = 0;
   int bb = 0;
-  const uint64_t adesc0 = smem_desc(sA_addr), bdesc0 = smem_desc(sB_addr);
+  const uint64_t adesc0 = smem_desc(sA_addr), bdesc0 = smem_desc(sA_addr + kOffB);
+  const uint64_t adesc_tie = smem_desc_noswz(sA_addr + kOffTieA, 128, 0), bdesc_tie = smem_desc_noswz(sA_addr + kOffTieB, 0, 128);
   for (int k = k0 + slot; k < k0 + kc; k += n_slots) {
     const KfEntry kf = kfs[k];
     if (!kf_eligible(fr.cur_id, kf.frame_id, kb) || kf.n <= 0) continue;
@@ -233,6 +260,7 @@ __device__ __forceinline__ void mma_issuer(const KfEntry* __restrict__ kfs, int 
               const uint32_t kbo = (uint32_t)(s >> 2) * (kTN * 128) + (uint32_t)(s & 3) * 32;
               umma_i8(d, adesc + (ka >> 4), bdesc + (kbo >> 4), idesc, s > 0 ? 1u : 0u);
             }
+            umma_i8(d, adesc_tie, bdesc_tie, idesc, 1u);  // + (127 - column): the tie-break
             umma_commit(&acc_full[m]);
           }
         }
@@ -252,16 +280,16 @@ __device__ __forceinline__ void mma_issuer(const KfEntry* __restrict__ kfs, int 
 }
 
 // ---------------------------------------------------------------- the kernel
-// grid.x = n_ablocks * n_slots; CTA (a, slot) matches A-block a against keyframes k0 + slot, + n_slots, ...
+// One CTA per CtaWork entry: query block `ablock` against keyframes k0 + slot, k0 + slot + n_slots, ...
 // scratch[(frame * kc + (k - k0)) * stride + q] = dist << 20 | row  for every compared (frame, k, q).
 __global__ void __launch_bounds__(kThreads, 1)
     tensor_match_kernel(const KfEntry* __restrict__ kfs, int k0, int kc, const QFrame* __restrict__ frames,
-                        const ABlock* __restrict__ blocks, int n_ablocks, uint32_t* __restrict__ scratch, int scratch_stride,
-                        Knobs kb) {
+                        const ABlock* __restrict__ blocks, const CtaWork* __restrict__ work, uint32_t* __restrict__ scratch,
+                        int scratch_stride, Knobs kb) {
   extern __shared__ __align__(1024) uint8_t smem[];  // SWIZZLE_128B operands need 1024-byte alignment
   uint8_t* sA = smem;
-  uint8_t* sB = smem + kABytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kABytes + kBStages * kBTileBytes);
+  uint8_t* sB = smem + kOffB;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kOffBar);
   uint64_t* a_full = bars;                          // 1 arrival + tx bytes
   uint64_t* b_full = bars + 1;                      // [kBStages] one arrival per expander thread
   uint64_t* b_empty = b_full + kBStages;            // [kBStages] one commit per MMA issuer warp
@@ -270,8 +298,9 @@ __global__ void __launch_bounds__(kThreads, 1)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + kAccStages);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int a = blockIdx.x % n_ablocks, slot = blockIdx.x / n_ablocks, n_slots = gridDim.x / n_ablocks;
-  const ABlock ab = blocks[a];
+  const CtaWork cw = work[blockIdx.x];
+  const int slot = cw.slot, n_slots = cw.n_slots;
+  const ABlock ab = blocks[cw.ablock];
   const QFrame fr = frames[ab.frame];
   const int nq_blk = min(kQPerCta, fr.nq - ab.q0);            // queries of this block (> 0 by construction)
   const int m_tiles = (nq_blk + kQTile - 1) / kQTile;
@@ -289,6 +318,12 @@ __global__ void __launch_bounds__(kThreads, 1)
     }
     mbar_fence_init();
   }
+  // constant operands of the tie-break MMA step: A = 1 at k = 0 (every row), B = 127 - column at k = 0
+  for (int i = threadIdx.x; i < (kTieABytes + kTieBBytes) / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem + kOffTieA)[i] = 0u;
+  __syncthreads();
+  if (threadIdx.x < 8) smem[kOffTieA + threadIdx.x * 16] = 1;  // K-chunk 0, row r at +16 r, k = 0 is its first byte
+  if (threadIdx.x < kTN) smem[kOffTieB + (threadIdx.x >> 3) * 128 + (threadIdx.x & 7) * 16] = (uint8_t)(kTN - 1 - threadIdx.x);
+  fence_proxy_async();  // generic-proxy stores -> visible to the tensor core's async-proxy reads
   if (warp == kMmaWarp) tmem_alloc(tmem_slot, kTmemCols);
   tc_fence_before();
   __syncthreads();
@@ -303,9 +338,9 @@ __global__ void __launch_bounds__(kThreads, 1)
     }
     __syncwarp();
     if (warp == kMmaWarp)
-      mma_issuer<0>(kfs, k0, kc, slot, n_slots, fr, kb, m_tiles, tmem_base, smem_u32(sA), smem_u32(sB), a_full, b_full, b_empty, acc_full, acc_empty);
+      mma_issuer<0>(kfs, k0, kc, slot, n_slots, fr, kb, m_tiles, tmem_base, smem_u32(sA), a_full, b_full, b_empty, acc_full, acc_empty);
     else
-      mma_issuer<1>(kfs, k0, kc, slot, n_slots, fr, kb, m_tiles, tmem_base, smem_u32(sA), smem_u32(sB), a_full, b_full, b_empty, acc_full, acc_empty);
+      mma_issuer<1>(kfs, k0, kc, slot, n_slots, fr, kb, m_tiles, tmem_base, smem_u32(sA), a_full, b_full, b_empty, acc_full, acc_empty);
   } else if (warp >= kEpiWarps) {
     // ===================== B expanders (128 threads) =====================
     const int et = threadIdx.x - kEpiWarps * 32;
@@ -332,8 +367,8 @@ __global__ void __launch_bounds__(kThreads, 1)
           if (idx < nwords) {
             uint32_t o0, o1;
             tile_offsets(kTN, idx >> 3, idx & 7, o0, o1);
-            *reinterpret_cast<uint4*>(tile + o0) = expand_half(bits[i] & 0xffffu);
-            *reinterpret_cast<uint4*>(tile + o1) = expand_half(bits[i] >> 16);
+            *reinterpret_cast<uint4*>(tile + o0) = expand_half<1>(bits[i] & 0xffffu);
+            *reinterpret_cast<uint4*>(tile + o1) = expand_half<1>(bits[i] >> 16);
           }
         }
         fence_proxy_async();  // generic-proxy stores -> visible to the tensor core's async-proxy reads
@@ -347,37 +382,39 @@ __global__ void __launch_bounds__(kThreads, 1)
     const int row = quad * 32 + lane;  // row inside an A tile
     const int c0 = half * kColsPerEpiWarp;
     uint32_t par_accfull = 0;  // accumulator stage == m: every stage completes once per B tile
-    const int unit = (int)kb.key_unit;
     for (int k = k0 + slot; k < k0 + kc; k += n_slots) {
       const KfEntry kf = kfs[k];
       if (!kf_eligible(fr.cur_id, kf.frame_id, kb) || kf.n <= 0) continue;
-      int best[kQTilesPerCta];
+      uint32_t best[kQTilesPerCta];  // dist << 20 | row, smaller is better
 #pragma unroll
-      for (int m = 0; m < kQTilesPerCta; ++m) best[m] = (int)0x80000000;
+      for (int m = 0; m < kQTilesPerCta; ++m) best[m] = 0xffffffffu;
       for (int row0 = 0; row0 < kf.n; row0 += kTN) {
         const int cnt = min(kTN, kf.n - row0);
-#pragma unroll 1
-        for (int m = 0; m < m_tiles; ++m) {
-          mbar_wait_guard(&acc_full[m], par_accfull);
-          tc_fence_after();
-          const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)m * kAccStride;
-          int tkey = (int)0x80000000;
-          if (kb.debug == 0) tkey = fold_accumulator(taddr, c0, cnt, unit);  // the loads have completed when this returns
-          tc_fence_before();
-          mbar_arrive(&acc_empty[m]);  // accumulator stage drained by this thread
-          if (tkey != (int)0x80000000) best[m] = max(best[m], tkey + ((int)kKeyRowMask - row0));
+#pragma unroll
+        for (int m = 0; m < kQTilesPerCta; ++m) {
+          if (m < m_tiles) {
+            mbar_wait_guard(&acc_full[m], par_accfull);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)m * kAccStride;
+            const int dmax = fold_accumulator(taddr, c0, cnt);  // the TMEM loads have completed when this returns
+            tc_fence_before();
+            mbar_arrive(&acc_empty[m]);  // accumulator stage drained by this thread
+            if (dmax != (int)0x80000000) {
+              // D' = 127 * dot + tie, dot = 256 - 2 * ham, tie = 127 - column  =>  D' + 127 * 256 = 254 * (256 - ham) + tie
+              const uint32_t u = (uint32_t)(dmax + 127 * 256);
+              const uint32_t h = u / 254u, tie = u - h * 254u;
+              best[m] = min(best[m], ((256u - h) << kKeyShift) | (uint32_t)(row0 + (kTN - 1) - (int)tie));
+            }
+          }
         }
         par_accfull ^= 1;
       }
-      // the two column halves of a row meet in scratch: dist << 20 | row, smaller is better
+      // the two column halves of a row meet in scratch
       uint32_t* dst = scratch + ((size_t)ab.frame * kc + (k - k0)) * scratch_stride + ab.q0;
-      for (int m = 0; m < m_tiles; ++m) {
+#pragma unroll
+      for (int m = 0; m < kQTilesPerCta; ++m) {
         const int q = m * kQTile + row;
-        if (q < nq_blk && best[m] != (int)0x80000000) {
-          const int dot = best[m] >> kKeyShift;  // arithmetic shift: key = dot * 2^20 + (2^20 - 1 - row)
-          const uint32_t r = kKeyRowMask - ((uint32_t)best[m] & kKeyRowMask);
-          atomicMin(dst + q, ((uint32_t)((256 - dot) >> 1) << kKeyShift) | r);
-        }
+        if (m < m_tiles && q < nq_blk && best[m] != 0xffffffffu) atomicMin(dst + q, best[m]);
       }
     }
   }
