@@ -204,7 +204,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="c4", choices=sorted(WORKLOADS))
     ap.add_argument("--keyframes", type=int, default=0, help="override the workload's keyframe count")
-    ap.add_argument("--kernel", default="auto", choices=["auto", "popc", "csa", "tensor"])
+    ap.add_argument("--kernel", default="auto", choices=["auto", "popc", "csa", "tensor", "mxf4"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extra", action="store_true")
     args = ap.parse_args()
@@ -243,7 +243,7 @@ def main():
 
     wl = WORKLOADS[args.workload]
     n_kf = args.keyframes or wl["keyframes"]
-    kernel = {"auto": lc.KERNEL_AUTO, "popc": lc.KERNEL_POPC, "csa": lc.KERNEL_CSA, "tensor": lc.KERNEL_TENSOR}[args.kernel]
+    kernel = {"auto": lc.KERNEL_AUTO, "popc": lc.KERNEL_POPC, "csa": lc.KERNEL_CSA, "tensor": lc.KERNEL_TENSOR, "mxf4": lc.KERNEL_MXF4}[args.kernel]
     cur_id = n_kf + 29  # every keyframe is at least min_loop_gap back
     q = query_rows()
     db = ShardedLoopDB(device=local, loop_threshold=0.15, kernel=kernel)
@@ -359,7 +359,7 @@ def main():
         "config": {"workload": wl["name"] if not args.keyframes else f"{n_kf}-keyframe DB x {ROWS_PER_KF} rows", "keyframes": n_kf,
                    "rows_per_keyframe": ROWS_PER_KF, "nq": NQ, "pairs_per_step": pairs_per_step,
                    "sharding": f"keyframe k -> rank k % {world}; NCCL all_reduce(MIN) u64 + all_gather per step" if world > 1 else "single GPU",
-                   "kernel": args.kernel, "path": {1: "whole-keyframe scan", 2: "split + finalize", 3: "tcgen05 int8 GEMM + arg-max"}.get(timing.path, "?"),
+                   "kernel": args.kernel, "path": {1: "whole-keyframe scan", 2: "split + finalize", 3: "tcgen05 int8 GEMM + arg-max", 4: "tcgen05 mxf4 GEMM + max, best row resolved afterwards"}.get(timing.path, "?"),
                    "l2": f"inputs larger than L2: each step streams the {sizes['local_rows'] * 32 / 1e9:.2f} GB DB shard from HBM"},
         "e2e": {"value": pairs_per_step * args.steps / (e2e_ms * 1e-3) / 1e9, "unit": "Gpairs/s", "ms_per_step": e2e_ms / args.steps,
                 "h2d_bytes_per_step": NQ * 32, "d2h_bytes_per_step": int(n_kf * 16 + NQ * 8) if world == 1 else int((n_kf + world) * 16 + NQ * 8),

@@ -47,12 +47,15 @@ typedef enum lc_status {
 } lc_status;
 
 typedef enum lc_kernel {
-  LC_KERNEL_AUTO = 0, /* library default: the measured-fastest bit-exact path (tensor cores when the problem fills
+  LC_KERNEL_AUTO = 0, /* library default: the measured-fastest bit-exact path (LC_KERNEL_MXF4 when the problem fills
                          the GPU, else the carry-save integer kernels) */
   LC_KERNEL_POPC = 1, /* 8 x (XOR, POPC) per pair: the naive integer-popc formulation */
   LC_KERNEL_CSA = 2,  /* carry-save adder tree: 16 LOP3 + 4 POPC per pair, same result */
-  LC_KERNEL_TENSOR = 3 /* tcgen05.mma kind::i8 on +1/-1 expanded bits (dot = 256 - 2*hamming) + arg-max epilogue, same
-                          result; problems too small to fill the GPU use the CSA kernels */
+  LC_KERNEL_TENSOR = 3, /* tcgen05.mma kind::i8 on +1/-1 expanded bits (dot = 256 - 2*hamming) + arg-max epilogue, same
+                           result; problems too small to fill the GPU use the CSA kernels */
+  LC_KERNEL_MXF4 = 4    /* tcgen05.mma kind::mxf4 on E2M1 +1/-1 expanded bits (unit block scales, exact f32 sums): twice
+                           the int8 rate; the kernel keeps distances only and the per-query best row is recovered on
+                           the winning keyframe afterwards; same result */
 } lc_kernel;
 
 /* Parameters of the path.  Defaults (lc_default_config) follow the reference header and README;
@@ -102,7 +105,7 @@ typedef struct lc_timing {
   float d2h_ms;    /* device -> pinned results */
   float total_ms;  /* first H2D to last D2H on the stream */
   int32_t kernel_launches;
-  int32_t path;    /* 1 = whole-keyframe scan kernel, 2 = split kernel + finalize, 3 = tensor-core kernel + finalize */
+  int32_t path;    /* 1 = whole-keyframe scan kernel, 2 = split kernel + finalize, 3 = int8 tensor-core kernel + finalize, 4 = FP4 tensor-core kernel + finalize + resolve */
 } lc_timing;
 
 int32_t lc_abi_version(void);

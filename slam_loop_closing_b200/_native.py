@@ -17,7 +17,7 @@ KF_RESULT = np.dtype([("frame_id", "<i4"), ("n_kf", "<i4"), ("min_dist", "<i4"),
 LOOP_CANDIDATE = np.dtype([("current_frame_id", "<i4"), ("matched_frame_id", "<i4"), ("num_matches", "<i4"),
                            ("similarity_score", "<f8")], align=True)
 
-KERNEL_AUTO, KERNEL_POPC, KERNEL_CSA, KERNEL_TENSOR = 0, 1, 2, 3
+KERNEL_AUTO, KERNEL_POPC, KERNEL_CSA, KERNEL_TENSOR, KERNEL_MXF4 = 0, 1, 2, 3, 4
 
 
 class Config(C.Structure):

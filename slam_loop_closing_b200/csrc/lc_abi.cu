@@ -17,6 +17,7 @@
 
 #include "lc_kernels.cuh"
 #include "lc_tensor.cuh"
+#include "lc_mxf4.cuh"
 
 using namespace lc;
 
@@ -130,12 +131,12 @@ Knobs knobs_of(const lc_config& g) {
   return Knobs{g.min_loop_gap, g.gap_strict, g.filter_floor, g.filter_strict, g.min_init, 1u << kKeyShift};
 }
 
-int mode_of(const lc_config& g) { return g.kernel == LC_KERNEL_POPC ? MODE_POPC : MODE_CSA; }  // the tensor path falls back to CSA for tiny problems
+int mode_of(const lc_config& g) { return g.kernel == LC_KERNEL_POPC ? MODE_POPC : MODE_CSA; }  // the tensor paths fall back to CSA for tiny problems
 
 int validate(lc_ctx* c, const lc_config& g) {
   if (g.shard_world < 1 || g.shard_rank < 0 || g.shard_rank >= g.shard_world)
     return fail(c, LC_ERR_INVALID, "shard_rank %d / shard_world %d invalid", g.shard_rank, g.shard_world);
-  if (g.kernel < LC_KERNEL_AUTO || g.kernel > LC_KERNEL_TENSOR) return fail(c, LC_ERR_INVALID, "unknown kernel %d", g.kernel);
+  if (g.kernel < LC_KERNEL_AUTO || g.kernel > LC_KERNEL_MXF4) return fail(c, LC_ERR_INVALID, "unknown kernel %d", g.kernel);
   if (g.slab_rows < 0) return fail(c, LC_ERR_INVALID, "slab_rows < 0");
   if (g.min_loop_gap < -(1 << 30) || g.min_loop_gap > (1 << 30)) return fail(c, LC_ERR_INVALID, "min_loop_gap out of range");
   return LC_OK;
@@ -287,41 +288,50 @@ int run_match(lc_ctx* c, cudaStream_t st, const KfEntry* d_kfs, int n_kf, int ma
   for (int f = 0; f < n_frames; ++f) max_nq = std::max(max_nq, h_frames[f].nq);
   const int mode = mode_of(c->cfg);
 
-  // ---- tensor cores: int8 GEMM + arg-max (lc_tensor.cuh) when there is a machine's worth of work
-  const bool want_tensor = c->cfg.kernel == LC_KERNEL_TENSOR || c->cfg.kernel == LC_KERNEL_AUTO;
-  if (want_tensor && !force_split && max_nq > 0 && max_rows > 0) {
-    std::vector<tc::ABlock> blocks;
+  // ---- tensor cores when there is a machine's worth of work: FP4 GEMM + max (lc_mxf4.cuh, the default) or int8 GEMM
+  //      + arg-max (lc_tensor.cuh)
+  const int kern = c->cfg.kernel;
+  const bool want_fp4 = kern == LC_KERNEL_MXF4 || kern == LC_KERNEL_AUTO, want_i8 = kern == LC_KERNEL_TENSOR;
+  if ((want_fp4 || want_i8) && !force_split && max_nq > 0 && max_rows > 0) {
+    const int q_per_cta = want_fp4 ? fx::kQPerCta : tc::kQPerCta;
+    const size_t img_bytes = want_fp4 ? (size_t)fx::kABytes : (size_t)tc::kABytes;
+    std::vector<tc::ABlock> blocks;  // fx::ABlock has the same layout
+    static_assert(sizeof(tc::ABlock) == sizeof(fx::ABlock), "ABlock layouts differ");
     std::vector<int> tiles;
     long long total_tiles = 0;
     for (int f = 0; f < n_frames; ++f)
-      for (int q0 = 0; q0 < h_frames[f].nq; q0 += tc::kQPerCta) {
+      for (int q0 = 0; q0 < h_frames[f].nq; q0 += q_per_cta) {
         blocks.push_back(tc::ABlock{nullptr, f, q0});
-        tiles.push_back((std::min(tc::kQPerCta, h_frames[f].nq - q0) + tc::kQTile - 1) / tc::kQTile);
+        tiles.push_back((std::min(q_per_cta, h_frames[f].nq - q0) + tc::kQTile - 1) / tc::kQTile);
         total_tiles += tiles.back();
       }
     const int n_ab = (int)blocks.size();
     if ((long long)n_ab * n_kf >= c->num_sms) {
-      // CTAs per query block: proportional to its number of 128-row tiles (a ragged last block gets fewer), about one
-      // CTA per SM in total; with more query blocks than SMs, enough CTAs for >= 4 waves
+      // CTAs per query block: proportional to its number of 128-row tiles (a ragged last block gets fewer); about one
+      // CTA per SM in total while the blocks fit in half the machine, else enough CTAs for >= 4 waves
+      const long long target = 2 * n_ab <= c->num_sms ? c->num_sms : 4ll * c->num_sms;
       std::vector<tc::CtaWork> work;
       for (int i = 0; i < n_ab; ++i) {
-        long long ns = n_ab <= c->num_sms ? std::max<long long>(1, ((long long)c->num_sms * tiles[i]) / total_tiles)
-                                          : (4ll * c->num_sms + n_ab - 1) / n_ab;
+        long long ns = std::max<long long>(1, (target * tiles[i]) / total_tiles);
         ns = std::min<long long>(ns, n_kf);
         for (int s = 0; s < (int)ns; ++s) work.push_back(tc::CtaWork{i, s, (int)ns});
       }
-      LC_TRY(ensure(c, c->d_qimg, (size_t)n_ab * tc::kABytes));
+      LC_TRY(ensure(c, c->d_qimg, (size_t)n_ab * img_bytes));
       LC_TRY(ensure(c, c->d_ablocks, (size_t)n_ab * sizeof(tc::ABlock) + work.size() * sizeof(tc::CtaWork)));
-      for (int i = 0; i < n_ab; ++i) blocks[i].img = (const uint8_t*)c->d_qimg.p + (size_t)i * tc::kABytes;
+      for (int i = 0; i < n_ab; ++i) blocks[i].img = (const uint8_t*)c->d_qimg.p + (size_t)i * img_bytes;
       tc::ABlock* d_blocks = (tc::ABlock*)c->d_ablocks.p;
       tc::CtaWork* d_work = (tc::CtaWork*)(d_blocks + n_ab);
       LC_CUDA(c, cudaMemcpyAsync(d_blocks, blocks.data(), (size_t)n_ab * sizeof(tc::ABlock), cudaMemcpyHostToDevice, st));
       LC_CUDA(c, cudaMemcpyAsync(d_work, work.data(), work.size() * sizeof(tc::CtaWork), cudaMemcpyHostToDevice, st));
-      tc::expand_queries_kernel<<<n_ab, 256, 0, st>>>(d_blocks, d_frames, (uint8_t*)c->d_qimg.p);
+      if (want_fp4)
+        fx::expand_queries_fp4_kernel<<<n_ab, 512, 0, st>>>((const fx::ABlock*)d_blocks, d_frames, (uint8_t*)c->d_qimg.p);
+      else
+        tc::expand_queries_kernel<<<n_ab, 256, 0, st>>>(d_blocks, d_frames, (uint8_t*)c->d_qimg.p);
       LC_CUDA(c, cudaGetLastError());
       static bool attr_set = false;
       if (!attr_set) {
         LC_CUDA(c, cudaFuncSetAttribute(tc::tensor_match_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kSmemAlloc));
+        LC_CUDA(c, cudaFuncSetAttribute(fx::mxf4_match_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, fx::kSmemAlloc));
         attr_set = true;
       }
       const int stride = (max_nq + 3) & ~3;
@@ -332,17 +342,41 @@ int run_match(lc_ctx* c, cudaStream_t st, const KfEntry* d_kfs, int n_kf, int ma
       c->timing.kernel_launches += 1;
       for (int k0 = 0; k0 < n_kf; k0 += (int)kc_max) {
         const int kc = (int)std::min<long long>(kc_max, n_kf - k0);
-        LC_CUDA(c, cudaMemsetAsync(c->d_scratch.p, 0xff, (size_t)kc * n_frames * stride * 4, st));
-        tc::tensor_match_kernel<<<(unsigned)work.size(), tc::kThreads, tc::kSmemAlloc, st>>>(
-            d_kfs, k0, kc, d_frames, d_blocks, d_work, (uint32_t*)c->d_scratch.p, stride, kb);
-        LC_CUDA(c, cudaGetLastError());
-        finalize_kernel<<<kc * n_frames, 256, 0, st>>>(d_kfs, n_kf, k0, kc, d_frames, (const uint32_t*)c->d_scratch.p, stride,
-                                                       d_results, po.train_idx, po.dist, po.good, po.summary, kb);
+        if (want_fp4) {
+          // every compared (frame, keyframe, query) distance is stored exactly once: no scratch initialisation
+          fx::mxf4_match_kernel<<<(unsigned)work.size(), fx::kThreads, fx::kSmemAlloc, st>>>(
+              d_kfs, k0, kc, d_frames, (const fx::ABlock*)d_blocks, d_work, (uint32_t*)c->d_scratch.p, stride, kb);
+          LC_CUDA(c, cudaGetLastError());
+          fx::finalize_dist_kernel<<<kc * n_frames, 256, 0, st>>>(d_kfs, n_kf, k0, kc, d_frames, (const uint32_t*)c->d_scratch.p,
+                                                                 stride, d_results, kb);
+        } else {
+          LC_CUDA(c, cudaMemsetAsync(c->d_scratch.p, 0xff, (size_t)kc * n_frames * stride * 4, st));
+          tc::tensor_match_kernel<<<(unsigned)work.size(), tc::kThreads, tc::kSmemAlloc, st>>>(
+              d_kfs, k0, kc, d_frames, d_blocks, d_work, (uint32_t*)c->d_scratch.p, stride, kb);
+          LC_CUDA(c, cudaGetLastError());
+          finalize_kernel<<<kc * n_frames, 256, 0, st>>>(d_kfs, n_kf, k0, kc, d_frames, (const uint32_t*)c->d_scratch.p, stride,
+                                                         d_results, po.train_idx, po.dist, po.good, po.summary, kb);
+        }
         LC_CUDA(c, cudaGetLastError());
         c->launches += 2;
         c->timing.kernel_launches += 2;
       }
-      c->timing.path = 3;
+      if (want_fp4) {
+        bool any_best = false;
+        long long total_nq = 0;
+        for (int f = 0; f < n_frames; ++f) {
+          any_best = any_best || h_frames[f].best_packed != nullptr;
+          total_nq += h_frames[f].nq;
+        }
+        if (any_best) {  // winning keyframe of each query -> winning row (OpenCV's lowest-index order)
+          const int grid = (int)std::min<long long>((total_nq + 7) / 8, 4ll * c->num_sms);
+          fx::resolve_best_kernel<<<std::max(grid, 1), 256, 0, st>>>(d_kfs, d_frames, n_frames);
+          LC_CUDA(c, cudaGetLastError());
+          c->launches += 1;
+          c->timing.kernel_launches += 1;
+        }
+      }
+      c->timing.path = want_fp4 ? 4 : 3;
       return LC_OK;
     }
   }

@@ -1,0 +1,434 @@
+// lc_mxf4.cuh - Hamming matching on the FP4 tensor pipe (tcgen05.mma kind::mxf4.block_scale, TMEM).
+//
+// Identity: descriptor bits mapped to E2M1 +1.0 / -1.0 (all UE8M0 block scales = 1.0) give
+//     D[q][t] = 256 - 2 * hamming(q, t)          (f32 accumulation of <= 256 terms of +/-1: exact),
+// so min_t hamming = (256 - max_t D) / 2.  kind::mxf4 runs 16384 MAC/clk/SM = 64 descriptor pairs/clk/SM, twice
+// kind::i8 and 32x the POPC pipe (measured: tools/umma_fp4.cu, profiles/r01_umma_fp4_probe.txt).
+//
+// What this kernel produces is the per-(keyframe, query) MINIMUM DISTANCE only.  That is all the loop check needs per
+// keyframe (min_dist, 2 x min filter, n_good: README.md:117-126); the train index is needed once per query, for the
+// global best over the whole DB, and is recovered afterwards by resolve_best_kernel on the single winning keyframe
+// of each query (lowest keyframe, then lowest row: OpenCV's order).  Dropping the index from the hot loop removes
+// the tie-break MMA step of lc_tensor.cuh (1/5 of the MMA time here) and leaves a plain FMNMX3 fold as epilogue.
+//
+// Shape (all measured on B200):
+//   * M = 128 queries x N = 224 train rows x K = 64 per MMA, 4 MMAs per tile.  One mxf4 MMA costs
+//     max(111, N / 2) cycles with both operands in shared memory, so N = 224 is the smallest full-rate tile; two
+//     224-column f32 accumulators + the scale-factor cells fill TMEM's 512 columns.
+//   * A (queries) is RESIDENT: one CTA owns up to 1024 queries = 8 tiles x 16 KiB (a packed E2M1 row of 256 values is
+//     128 B = one SWIZZLE_128B row), written once by expand_queries_fp4_kernel and pulled in with bulk copies.
+//   * B (keyframe rows) is expanded IN the kernel from the 32-byte rows in HBM (the store stays 32 B/row): 4 expander
+//     warps, 9 ALU ops per 32 descriptor bits (PRMT as a 2-bit -> byte lookup), 3 stages of 28 KiB.  A B tile is
+//     reused by all resident A tiles.
+//   * 8 epilogue warps (TMEM lane quadrant x column half) read the accumulator with tcgen05.ld (257 B/clk/SM
+//     measured = 64 values/clk/SM: exactly the MMA rate, so the two pipes are co-critical) and fold 112 columns into
+//     one running maximum per query with FMNMX3.
+//   * one MMA issuer warp; mbarriers + tcgen05.commit connect the three roles.
+// Output: scratch[(frame * kc + (k - k0)) * stride + q] = min distance, plain stores, every compared (frame, k, q)
+// written exactly once - no memset, no atomics.
+#pragma once
+#include "lc_tensor.cuh"
+
+namespace lc {
+namespace fx {
+
+using tc::elect_one;
+using tc::fence_proxy_async;
+using tc::mbar_arrive;
+using tc::mbar_wait_guard;
+using tc::tc_fence_after;
+using tc::tc_fence_before;
+using tc::tmem_ld32;
+using tc::tmem_ld_wait;
+using tc::umma_commit;
+
+constexpr int kQTile = 128;                  // UMMA M
+constexpr int kQTilesPerCta = 8;             // resident A tiles
+constexpr int kQPerCta = kQTile * kQTilesPerCta;  // 1024
+constexpr int kTN = 224;                     // train rows per B tile (UMMA N of a full tile)
+constexpr int kBStages = 3;
+constexpr int kAccStages = 2;
+constexpr int kAccStride = 256;              // TMEM columns between accumulator stages
+constexpr int kSfCol = 224;                  // TMEM columns [224, 256): scale-factor cells, all UE8M0 1.0
+constexpr int kATileBytes = kQTile * 128;    // 16 KiB
+constexpr int kBTileBytes = kTN * 128;       // 28 KiB
+constexpr int kABytes = kQTilesPerCta * kATileBytes;  // 128 KiB
+constexpr int kOffB = kABytes;
+constexpr int kOffXch = kOffB + kBStages * kBTileBytes;
+constexpr int kXchBytes = 2 * kQTilesPerCta * kQTile * 4;  // [parity][tile][row] f32: the column halves meet here
+constexpr int kOffBar = kOffXch + kXchBytes;
+constexpr int kBarBytes = 256;
+constexpr int kSmemAlloc = kOffBar + kBarBytes;  // 225,536 B of the 232,448 B a CTA may have
+constexpr int kEpiWarps = 8;                 // warp w: TMEM lane quadrant w % 4, column half w / 4
+constexpr int kExpWarps = 4;
+constexpr int kMmaWarp = kEpiWarps + kExpWarps;
+constexpr int kThreads = (kMmaWarp + 1) * 32;  // 416: warps 0-7 epilogue, 8-11 expanders, 12 MMA issuer
+constexpr int kTmemCols = 512;
+constexpr int kWordsPerExpThread = kTN * 8 / (kExpWarps * 32);  // 14
+constexpr uint32_t kNoDist = 0xffffu;
+
+struct ABlock {          // one resident query block: up to 1024 queries of one frame
+  const uint8_t* img;    // expanded smem image (kABytes), written by expand_queries_fp4_kernel
+  int32_t frame;
+  int32_t q0;
+};
+using tc::CtaWork;
+
+// ---------------------------------------------------------------- bit -> E2M1 expansion
+// 32 descriptor bits -> 32 E2M1 nibbles (one 16-byte swizzle chunk): bit clear -> +1.0 (0x2), bit set -> -1.0 (0xA).
+// PRMT is the lookup: a selector nibble holding two descriptor bits picks the byte (two E2M1 values) from the pool
+// {0x22, 0x2A, 0xA2, 0xAA}.  The resulting order of the 256 values along K is a fixed permutation of the bit order -
+// irrelevant for a dot product as long as queries and train rows use the same one.
+__device__ __forceinline__ uint4 expand_word_fp4(uint32_t x) {
+  constexpr uint32_t pool = 0xAAA22A22u;
+  const uint32_t lo = x & 0x33333333u, hi = (x >> 2) & 0x33333333u;
+  return make_uint4(__byte_perm(pool, 0u, lo & 0xffffu), __byte_perm(pool, 0u, lo >> 16), __byte_perm(pool, 0u, hi & 0xffffu),
+                    __byte_perm(pool, 0u, hi >> 16));
+}
+// byte offset of (row r, 32-bit descriptor word w) inside a K-major SWIZZLE_128B tile: row r at r * 128 B,
+// 16-byte chunk index XOR (row & 7)  (Swizzle<3,4,3>)
+__device__ __forceinline__ uint32_t tile_offset(int r, int w) { return (uint32_t)r * 128u + (((uint32_t)w ^ ((uint32_t)r & 7u)) << 4); }
+
+// one launch per loop check: every (frame, 1024-query block) gets its A image in global memory
+__global__ void expand_queries_fp4_kernel(const ABlock* __restrict__ blocks, const QFrame* __restrict__ frames, uint8_t* img_base) {
+  const ABlock ab = blocks[blockIdx.x];
+  const QFrame fr = frames[ab.frame];
+  uint8_t* img = img_base + (size_t)blockIdx.x * kABytes;
+  for (int idx = threadIdx.x; idx < kQPerCta * 8; idx += blockDim.x) {
+    const int ql = idx >> 3, w = idx & 7, q = ab.q0 + ql;
+    const uint32_t bits = q < fr.nq ? __ldg(reinterpret_cast<const uint32_t*>(fr.q) + (size_t)q * 8 + w) : 0u;
+    *reinterpret_cast<uint4*>(img + (size_t)(ql / kQTile) * kATileBytes + tile_offset(ql & (kQTile - 1), w)) = expand_word_fp4(bits);
+  }
+}
+
+// ---------------------------------------------------------------- PTX
+// D[tmem] (+)= A[smem] * B[smem]^T, E2M1 x E2M1 -> f32, block-32 UE8M0 scales read from TMEM; issued by ONE thread
+__device__ __forceinline__ void umma_mxf4(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate,
+                                          uint32_t tmem_sfa, uint32_t tmem_sfb) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::mxf4.block_scale.block32 [%0], %1, %2, %3, [%5], [%6], p;\n\t}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(tmem_sfa), "r"(tmem_sfb)
+      : "memory");
+}
+// block-scaled instruction descriptor: A, B = E2M1 (format 1), K-major, scales UE8M0 (bit 23), scale ids 0, M = 128, N = n
+__device__ __forceinline__ uint32_t instr_desc_mxf4(int n) {
+  return (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | (1u << 23) | ((uint32_t)(kQTile >> 4) << 24);
+}
+__device__ __forceinline__ void tmem_st1(uint32_t taddr, uint32_t v) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x1.b32 [%0], {%1};" ::"r"(taddr), "r"(v) : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, int (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory"); }
+
+__device__ __forceinline__ float fmax4(float a, float b, float c, float d, float e) { return fmaxf(fmaxf(fmaxf(a, b), c), fmaxf(d, e)); }
+
+// max over this thread's row of columns [c0, c0 + ncols) of one accumulator stage; ncols is a multiple of 16, <= 112.
+// All loads are issued before the single wait; independent running maxima keep the FMNMX3 chains short.
+__device__ __forceinline__ float fold_accumulator(uint32_t taddr, int ncols) {
+  constexpr float NEG = -1024.f;
+  float m0 = NEG, m1 = NEG, m2 = NEG, m3 = NEG;
+  if (ncols == kTN / 2) {  // the full tile: 112 = 32 + 32 + 32 + 16 columns
+    int v[112];
+    tmem_ld32(taddr, *reinterpret_cast<int (*)[32]>(&v[0]));
+    tmem_ld32(taddr + 32, *reinterpret_cast<int (*)[32]>(&v[32]));
+    tmem_ld32(taddr + 64, *reinterpret_cast<int (*)[32]>(&v[64]));
+    tmem_ld16(taddr + 96, *reinterpret_cast<int (*)[16]>(&v[96]));
+    tmem_ld_wait();
+#pragma unroll
+    for (int j = 0; j < 112; j += 8) {
+      m0 = fmaxf(m0, fmaxf(__int_as_float(v[j + 0]), __int_as_float(v[j + 1])));
+      m1 = fmaxf(m1, fmaxf(__int_as_float(v[j + 2]), __int_as_float(v[j + 3])));
+      m2 = fmaxf(m2, fmaxf(__int_as_float(v[j + 4]), __int_as_float(v[j + 5])));
+      m3 = fmaxf(m3, fmaxf(__int_as_float(v[j + 6]), __int_as_float(v[j + 7])));
+    }
+  } else {  // the last tile of a keyframe: 16 columns at a time
+#pragma unroll 1
+    for (int c = 0; c < ncols; c += 16) {
+      int v[16];
+      tmem_ld16(taddr + c, v);
+      tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 16; j += 8) {
+        m0 = fmaxf(m0, fmaxf(__int_as_float(v[j + 0]), __int_as_float(v[j + 1])));
+        m1 = fmaxf(m1, fmaxf(__int_as_float(v[j + 2]), __int_as_float(v[j + 3])));
+        m2 = fmaxf(m2, fmaxf(__int_as_float(v[j + 4]), __int_as_float(v[j + 5])));
+        m3 = fmaxf(m3, fmaxf(__int_as_float(v[j + 6]), __int_as_float(v[j + 7])));
+      }
+    }
+  }
+  return fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+}
+
+// columns of a tile with `cnt` valid rows: rounded up to 32 (pad rows are copies of the last valid row, so they never
+// change a maximum) - every column half is then a whole number of 16-column loads
+__device__ __forceinline__ int tile_cols(int cnt) { return (cnt + 31) & ~31; }
+
+// ---------------------------------------------------------------- the kernel
+// One CTA per CtaWork entry: query block `ablock` against keyframes k0 + slot, k0 + slot + n_slots, ...
+__global__ void __launch_bounds__(kThreads, 1)
+    mxf4_match_kernel(const KfEntry* __restrict__ kfs, int k0, int kc, const QFrame* __restrict__ frames,
+                      const ABlock* __restrict__ blocks, const CtaWork* __restrict__ work, uint32_t* __restrict__ scratch,
+                      int scratch_stride, Knobs kb) {
+  extern __shared__ __align__(1024) uint8_t smem[];  // SWIZZLE_128B operands need 1024-byte alignment
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + kOffB;
+  float* xch = reinterpret_cast<float*>(smem + kOffXch);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kOffBar);
+  uint64_t* a_full = bars;                          // 1 arrival + tx bytes
+  uint64_t* b_full = bars + 1;                      // [kBStages] one arrival per expander thread
+  uint64_t* b_empty = b_full + kBStages;            // [kBStages] 1 commit
+  uint64_t* acc_full = b_empty + kBStages;          // [kAccStages] 1 commit
+  uint64_t* acc_empty = acc_full + kAccStages;      // [kAccStages] one arrival per epilogue thread
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + kAccStages);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const CtaWork cw = work[blockIdx.x];
+  const int slot = cw.slot, n_slots = cw.n_slots;
+  const ABlock ab = blocks[cw.ablock];
+  const QFrame fr = frames[ab.frame];
+  const int nq_blk = min(kQPerCta, fr.nq - ab.q0);            // queries of this block (> 0 by construction)
+  const int m_tiles = (nq_blk + kQTile - 1) / kQTile;
+
+  if (threadIdx.x == 0) {
+    if (smem_u32(smem) & 1023u) __trap();
+    mbar_init(a_full, 1);
+    for (int i = 0; i < kBStages; ++i) {
+      mbar_init(&b_full[i], kExpWarps * 32);
+      mbar_init(&b_empty[i], 1);
+    }
+    for (int i = 0; i < kAccStages; ++i) {
+      mbar_init(&acc_full[i], 1);
+      mbar_init(&acc_empty[i], kEpiWarps * 32);
+    }
+    mbar_fence_init();
+  }
+  if (warp == kMmaWarp) tc::tmem_alloc(tmem_slot, kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  if (warp < 4) {  // scale factors: every cell of columns [224, 256) = four UE8M0 1.0 bytes, all 128 lanes
+    for (int c = 0; c < 32; ++c) tmem_st1(tmem_base + ((uint32_t)(warp * 32) << 16) + kSfCol + c, 0x7f7f7f7fu);
+    tmem_st_wait();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+
+  if (warp == kMmaWarp) {
+    // ===================== MMA issuer =====================
+    // The whole warp runs the (uniform) control flow so descriptors live in uniform registers; one elected lane
+    // issues tcgen05.mma / tcgen05.commit.
+    if (lane == 0) {
+      mbar_expect_tx(a_full, (uint32_t)m_tiles * kATileBytes);
+      for (int m = 0; m < m_tiles; ++m) bulk_g2s(sA + m * kATileBytes, ab.img + (size_t)m * kATileBytes, kATileBytes, a_full);
+    }
+    __syncwarp();
+    const bool leader = elect_one();
+    mbar_wait_guard(a_full, 0);
+    const uint64_t adesc0 = tc::smem_desc(smem_u32(sA)), bdesc0 = tc::smem_desc(smem_u32(sB));
+    const uint32_t sfa = tmem_base + kSfCol, sfb = tmem_base + kSfCol + 8;
+    uint32_t par_bfull = 0, n_btiles = 0, t = 0;  // t: accumulator tiles issued so far (stage t & 1)
+    int bb = 0;
+    for (int k = k0 + slot; k < k0 + kc; k += n_slots) {
+      const KfEntry kf = kfs[k];
+      if (!kf_eligible(fr.cur_id, kf.frame_id, kb) || kf.n <= 0) continue;
+      for (int row0 = 0; row0 < kf.n; row0 += kTN) {
+        const uint32_t idesc = instr_desc_mxf4(tile_cols(min(kTN, kf.n - row0)));
+        const uint64_t bdesc = bdesc0 + (uint64_t)((bb * kBTileBytes) >> 4);
+        mbar_wait_guard(&b_full[bb], (par_bfull >> bb) & 1);
+        par_bfull ^= 1u << bb;
+        tc_fence_after();
+#pragma unroll 1
+        for (int m = 0; m < m_tiles; ++m, ++t) {
+          mbar_wait_guard(&acc_empty[t & 1], ((t >> 1) & 1) ^ 1);
+          tc_fence_after();
+          if (leader) {
+            const uint32_t d = tmem_base + (t & 1) * kAccStride;
+            const uint64_t adesc = adesc0 + (uint64_t)((m * kATileBytes) >> 4);
+#pragma unroll
+            for (int s = 0; s < 4; ++s)  // K = 256 = 4 steps of 64 E2M1 values = 32 bytes along the 128-byte row
+              umma_mxf4(d, adesc + (uint64_t)(s * 2), bdesc + (uint64_t)(s * 2), idesc, s > 0 ? 1u : 0u, sfa, sfb);
+            umma_commit(&acc_full[t & 1]);
+          }
+          __syncwarp();
+        }
+        if (leader) umma_commit(&b_empty[bb]);  // arrives when the MMAs reading this B stage have completed
+        __syncwarp();
+        n_btiles += 1;
+        bb = bb + 1 == kBStages ? 0 : bb + 1;
+      }
+    }
+    // do not leave while a commit may still arrive on this CTA's barriers
+#pragma unroll
+    for (int i = 0; i < kBStages; ++i) {
+      const uint32_t n_i = (n_btiles + (kBStages - 1 - i)) / kBStages;  // phases completed on b_empty[i]
+      if (n_i) mbar_wait_guard(&b_empty[i], (n_i - 1) & 1);
+    }
+  } else if (warp >= kEpiWarps) {
+    // ===================== B expanders (128 threads) =====================
+    const int et = threadIdx.x - kEpiWarps * 32;
+    uint32_t par_bempty = (1u << kBStages) - 1;
+    int bb = 0;
+    for (int k = k0 + slot; k < k0 + kc; k += n_slots) {
+      const KfEntry kf = kfs[k];
+      if (!kf_eligible(fr.cur_id, kf.frame_id, kb) || kf.n <= 0) continue;
+      const uint32_t* words = reinterpret_cast<const uint32_t*>(kf.rows);
+      for (int row0 = 0; row0 < kf.n; row0 += kTN) {
+        const int cnt = min(kTN, kf.n - row0);
+        const int nwords = tile_cols(cnt) * 8;
+        uint32_t bits[kWordsPerExpThread];
+#pragma unroll
+        for (int i = 0; i < kWordsPerExpThread; ++i) {  // all loads in flight before the buffer is even free
+          const int idx = et + i * (kExpWarps * 32);
+          const int r = min(idx >> 3, cnt - 1);          // pad rows repeat the last valid row
+          bits[i] = idx < nwords ? __ldg(words + (size_t)(row0 + r) * 8 + (idx & 7)) : 0u;
+        }
+        mbar_wait_guard(&b_empty[bb], (par_bempty >> bb) & 1);
+        par_bempty ^= 1u << bb;
+        uint8_t* tile = sB + bb * kBTileBytes;
+#pragma unroll
+        for (int i = 0; i < kWordsPerExpThread; ++i) {
+          const int idx = et + i * (kExpWarps * 32);
+          if (idx < nwords) *reinterpret_cast<uint4*>(tile + tile_offset(idx >> 3, idx & 7)) = expand_word_fp4(bits[i]);
+        }
+        fence_proxy_async();  // generic-proxy stores -> visible to the tensor core's async-proxy reads
+        mbar_arrive(&b_full[bb]);
+        bb = bb + 1 == kBStages ? 0 : bb + 1;
+      }
+    }
+  } else {
+    // ===================== epilogue (256 threads: warp w owns TMEM lanes 32 (w % 4).., column half w / 4) ====
+    const int quad = warp & 3, half = warp >> 2;
+    const int row = quad * 32 + lane;  // row inside an A tile
+    uint32_t t = 0, kpar = 0;
+    for (int k = k0 + slot; k < k0 + kc; k += n_slots) {
+      const KfEntry kf = kfs[k];
+      if (!kf_eligible(fr.cur_id, kf.frame_id, kb) || kf.n <= 0) continue;
+      float best[kQTilesPerCta];
+#pragma unroll
+      for (int m = 0; m < kQTilesPerCta; ++m) best[m] = -1024.f;
+      for (int row0 = 0; row0 < kf.n; row0 += kTN) {
+        const int hcols = tile_cols(min(kTN, kf.n - row0)) >> 1;  // columns per half: a multiple of 16
+#pragma unroll
+        for (int m = 0; m < kQTilesPerCta; ++m) {
+          if (m < m_tiles) {
+            mbar_wait_guard(&acc_full[t & 1], (t >> 1) & 1);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (t & 1) * kAccStride + (uint32_t)(half * hcols);
+            const float dmax = fold_accumulator(taddr, hcols);  // the TMEM loads have completed when this returns
+            tc_fence_before();
+            mbar_arrive(&acc_empty[t & 1]);  // accumulator stage drained by this thread
+            best[m] = fmaxf(best[m], dmax);
+            ++t;
+          }
+        }
+      }
+      // the two column halves of a row meet in shared memory: half h hands over the tiles it does not finish
+      float* x = xch + kpar * (kQTilesPerCta * kQTile);
+#pragma unroll
+      for (int m = 0; m < kQTilesPerCta; ++m)
+        if ((m & 1) != half && m < m_tiles) x[m * kQTile + row] = best[m];
+      epi_bar_sync();
+      uint32_t* dst = scratch + ((size_t)ab.frame * kc + (k - k0)) * scratch_stride + ab.q0;
+#pragma unroll
+      for (int m = 0; m < kQTilesPerCta; ++m) {
+        const int q = m * kQTile + row;
+        if ((m & 1) == half && m < m_tiles && q < nq_blk) {
+          const float d = fmaxf(best[m], x[m * kQTile + row]);  // = 256 - 2 * min hamming
+          dst[q] = (uint32_t)(256 - (int)d) >> 1;
+        }
+      }
+      kpar ^= 1;  // the next keyframe writes the other exchange buffer: one barrier per keyframe is enough
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == kMmaWarp) {
+    tc_fence_after();
+    tc::tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+// ---------------------------------------------------------------- finalize (distance-only scratch)
+// one CTA per (frame, keyframe in [k0, k0 + kc)): min distance, 2 x min filter, count -> results[frame * n_kf + k];
+// per query, (dist << 32 | local keyframe index) is folded into best_packed - resolve_best_kernel turns the winning
+// keyframe into the winning row afterwards.
+__global__ void __launch_bounds__(256)
+    finalize_dist_kernel(const KfEntry* __restrict__ kfs, int n_kf, int k0, int kc, const QFrame* __restrict__ frames,
+                         const uint32_t* __restrict__ scratch, int scratch_stride, lc_kf_result* __restrict__ results, Knobs kb) {
+  __shared__ int red[8];
+  const int f = blockIdx.x / kc, k = k0 + (blockIdx.x - f * kc);
+  const int item = f * n_kf + k;
+  const QFrame fr = frames[f];
+  const KfEntry kf = kfs[k];
+  const int tid = threadIdx.x;
+  if (!kf_eligible(fr.cur_id, kf.frame_id, kb) || kf.n <= 0 || fr.nq <= 0) {
+    if (tid == 0) results[item] = lc_kf_result{kf.frame_id, kf.n, -1, -1};
+    return;
+  }
+  const uint32_t* dists = scratch + (size_t)blockIdx.x * scratch_stride;
+  int dmin = 0x7fffffff;
+  for (int i = tid; i < fr.nq; i += blockDim.x) dmin = min(dmin, (int)dists[i]);
+  dmin = block_min(dmin, red);
+  if (kb.min_init >= 0) dmin = min(dmin, kb.min_init);
+  const int thr = filter_threshold(dmin, kb);
+  int cnt_good = 0;
+  for (int i = tid; i < fr.nq; i += blockDim.x) {
+    const uint32_t d = dists[i];
+    cnt_good += is_good((int)d, thr, kb) ? 1 : 0;
+    if (fr.best_packed) {
+      const uint64_t packed = ((uint64_t)d << 32) | (uint32_t)k;
+      if (packed < *(volatile uint64_t*)(fr.best_packed + i)) atomicMin((unsigned long long*)(fr.best_packed + i), (unsigned long long)packed);
+    }
+  }
+  cnt_good = block_sum(cnt_good, red);
+  if (tid == 0) results[item] = lc_kf_result{kf.frame_id, kf.n, dmin, cnt_good};
+}
+
+// best_packed[i] = dist << 32 | local keyframe index  ->  dist << 32 | global row of the first row of that keyframe
+// at that distance (lowest keyframe, then lowest row: OpenCV's multi-image order).  One warp per query.
+__global__ void __launch_bounds__(256)
+    resolve_best_kernel(const KfEntry* __restrict__ kfs, const QFrame* __restrict__ frames, int n_frames) {
+  const int lane = threadIdx.x & 31;
+  const int wpb = blockDim.x >> 5;
+  for (int f = 0; f < n_frames; ++f) {
+    const QFrame fr = frames[f];
+    if (!fr.best_packed) continue;
+    for (int i = blockIdx.x * wpb + (threadIdx.x >> 5); i < fr.nq; i += gridDim.x * wpb) {
+      const uint64_t packed = fr.best_packed[i];
+      if (packed == ~0ull) continue;  // nothing was compared
+      const int d = (int)(packed >> 32);
+      const KfEntry kf = kfs[(uint32_t)packed];
+      const uint4 qa = __ldg(fr.q + 2 * (size_t)i), qb = __ldg(fr.q + 2 * (size_t)i + 1);
+      int found = -1;
+      for (int j0 = 0; j0 < kf.n && found < 0; j0 += 32) {
+        const int j = j0 + lane;
+        int dj = -1;
+        if (j < kf.n) {
+          const uint4 a = __ldg(kf.rows + 2 * (size_t)j), b = __ldg(kf.rows + 2 * (size_t)j + 1);
+          dj = __popc(qa.x ^ a.x) + __popc(qa.y ^ a.y) + __popc(qa.z ^ a.z) + __popc(qa.w ^ a.w) + __popc(qb.x ^ b.x) +
+               __popc(qb.y ^ b.y) + __popc(qb.z ^ b.z) + __popc(qb.w ^ b.w);
+        }
+        const uint32_t hit = __ballot_sync(0xffffffffu, dj == d);
+        if (hit) found = j0 + __ffs(hit) - 1;
+      }
+      if (found < 0) __trap();  // the distance came from this keyframe: a miss is a kernel bug
+      if (lane == 0) fr.best_packed[i] = ((uint64_t)d << 32) | (uint64_t)(kf.global_row_off + found);
+    }
+  }
+}
+
+}  // namespace fx
+}  // namespace lc

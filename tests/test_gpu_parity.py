@@ -199,7 +199,7 @@ def test_loop_scan_path_big_query_frames(lc):
         kfs = [datagen.uniform(24, 5000 + i) for i in range(5000)]
         fids = list(range(5000))
         p = Params(min_loop_gap=0)
-        for kernel, path in ((2, 1), (0, 3)):  # carry-save scan kernel; AUTO -> tensor cores
+        for kernel, path in ((2, 1), (0, 4)):  # carry-save scan kernel; AUTO -> tensor cores
             with _ctx(lc, p, kernel=kernel) as c:
                 c.db_append_many(fids, kfs)
                 _check_loop(c, q, kfs, fids, 6000, p, use_cv2=False)
@@ -211,7 +211,7 @@ def test_loop_query_larger_than_scan_capacity(lc):
     kfs = [datagen.low_entropy(50, 100 + i) for i in range(300)]
     fids = list(range(300))
     p = Params(min_loop_gap=1)
-    for kernel, path in ((2, 2), (0, 3)):  # split + finalize on the integer kernels; AUTO -> tensor cores
+    for kernel, path in ((2, 2), (0, 4)):  # split + finalize on the integer kernels; AUTO -> tensor cores
         with _ctx(lc, p, kernel=kernel) as c:
             c.db_append_many(fids, kfs)
             _check_loop(c, q, kfs, fids, 400, p, use_cv2=False)
