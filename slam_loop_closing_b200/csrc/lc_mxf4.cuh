@@ -20,9 +20,10 @@
 //   * B (keyframe rows) is expanded IN the kernel from the 32-byte rows in HBM (the store stays 32 B/row): 4 expander
 //     warps, 9 ALU ops per 32 descriptor bits (PRMT as a 2-bit -> byte lookup), 3 stages of 28 KiB.  A B tile is
 //     reused by all resident A tiles.
-//   * 8 epilogue warps (TMEM lane quadrant x column half) read the accumulator with tcgen05.ld (257 B/clk/SM
-//     measured = 64 values/clk/SM: exactly the MMA rate, so the two pipes are co-critical) and fold 112 columns into
-//     one running maximum per query with FMNMX3.
+//   * 8 epilogue warps (TMEM lane quadrant x column half) read the accumulator with tcgen05.ld (>= 341 B/clk/SM
+//     measured next to full-rate MMAs; 256 B/clk/SM are needed) and fold 112 columns into one running maximum per
+//     query with FMNMX3: 448 warp instructions per tile, a quarter of the SM's issue slots - with everything else
+//     the kernel is issue-bound as much as tensor-bound, so per-tile overhead instructions are kept minimal.
 //   * one MMA issuer warp; mbarriers + tcgen05.commit connect the three roles.
 // Output: scratch[(frame * kc + (k - k0)) * stride + q] = min distance, plain stores, every compared (frame, k, q)
 // written exactly once - no memset, no atomics.
@@ -34,13 +35,10 @@ namespace fx {
 
 using tc::elect_one;
 using tc::fence_proxy_async;
-using tc::mbar_arrive;
-using tc::mbar_wait_guard;
 using tc::tc_fence_after;
 using tc::tc_fence_before;
 using tc::tmem_ld32;
 using tc::tmem_ld_wait;
-using tc::umma_commit;
 
 constexpr int kQTile = 128;                  // UMMA M
 constexpr int kQTilesPerCta = 8;             // resident A tiles
@@ -64,8 +62,7 @@ constexpr int kExpWarps = 4;
 constexpr int kMmaWarp = kEpiWarps + kExpWarps;
 constexpr int kThreads = (kMmaWarp + 1) * 32;  // 416: warps 0-7 epilogue, 8-11 expanders, 12 MMA issuer
 constexpr int kTmemCols = 512;
-constexpr int kWordsPerExpThread = kTN * 8 / (kExpWarps * 32);  // 14
-constexpr uint32_t kNoDist = 0xffffu;
+constexpr int kPairsPerExpThread = kTN * 4 / (kExpWarps * 32);  // 7 descriptor word pairs per thread and B tile
 
 struct ABlock {          // one resident query block: up to 1024 queries of one frame
   const uint8_t* img;    // expanded smem image (kABytes), written by expand_queries_fp4_kernel
@@ -102,6 +99,29 @@ __global__ void expand_queries_fp4_kernel(const ABlock* __restrict__ blocks, con
 }
 
 // ---------------------------------------------------------------- PTX
+// Barriers are addressed by their 32-bit shared-window address, computed once: converting a generic pointer costs
+// five instructions per use, and this kernel is bound by instruction issue as much as by the tensor pipe.
+__device__ __forceinline__ bool mbar_try_a(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// bounded wait: a protocol bug must trap, not hang the GPU
+__device__ __forceinline__ void mbar_wait_a(uint32_t bar, uint32_t parity) {
+  for (uint32_t spins = 0; !mbar_try_a(bar, parity); ++spins)
+    if (spins > (1u << 24)) __trap();
+}
+__device__ __forceinline__ void mbar_arrive_a(uint32_t bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory"); }
+// mbarrier arrives once every tcgen05 op issued so far by this thread has completed
+__device__ __forceinline__ void umma_commit_a(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
 // D[tmem] (+)= A[smem] * B[smem]^T, E2M1 x E2M1 -> f32, block-32 UE8M0 scales read from TMEM; issued by ONE thread
 __device__ __forceinline__ void umma_mxf4(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate,
                                           uint32_t tmem_sfa, uint32_t tmem_sfb) {
@@ -131,43 +151,61 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, int (&v)[16]) {
 }
 __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory"); }
 
-__device__ __forceinline__ float fmax4(float a, float b, float c, float d, float e) { return fmaxf(fmaxf(fmaxf(a, b), c), fmaxf(d, e)); }
-
-// max over this thread's row of columns [c0, c0 + ncols) of one accumulator stage; ncols is a multiple of 16, <= 112.
-// All loads are issued before the single wait; independent running maxima keep the FMNMX3 chains short.
-__device__ __forceinline__ float fold_accumulator(uint32_t taddr, int ncols) {
-  constexpr float NEG = -1024.f;
-  float m0 = NEG, m1 = NEG, m2 = NEG, m3 = NEG;
-  if (ncols == kTN / 2) {  // the full tile: 112 = 32 + 32 + 32 + 16 columns
-    int v[112];
-    tmem_ld32(taddr, *reinterpret_cast<int (*)[32]>(&v[0]));
-    tmem_ld32(taddr + 32, *reinterpret_cast<int (*)[32]>(&v[32]));
-    tmem_ld32(taddr + 64, *reinterpret_cast<int (*)[32]>(&v[64]));
-    tmem_ld16(taddr + 96, *reinterpret_cast<int (*)[16]>(&v[96]));
-    tmem_ld_wait();
+// running maxima of one thread: four independent FMNMX3 chains
+struct Max4 {
+  float m0, m1, m2, m3;
+  __device__ __forceinline__ void reset() { m0 = m1 = m2 = m3 = -1024.f; }
+  template <int N>
+  __device__ __forceinline__ void fold(const int (&v)[N]) {
 #pragma unroll
-    for (int j = 0; j < 112; j += 8) {
+    for (int j = 0; j < N; j += 8) {
       m0 = fmaxf(m0, fmaxf(__int_as_float(v[j + 0]), __int_as_float(v[j + 1])));
       m1 = fmaxf(m1, fmaxf(__int_as_float(v[j + 2]), __int_as_float(v[j + 3])));
       m2 = fmaxf(m2, fmaxf(__int_as_float(v[j + 4]), __int_as_float(v[j + 5])));
       m3 = fmaxf(m3, fmaxf(__int_as_float(v[j + 6]), __int_as_float(v[j + 7])));
     }
+  }
+  __device__ __forceinline__ float get() const { return fmaxf(fmaxf(m0, m1), fmaxf(m2, m3)); }
+};
+
+// this warp has drained its part of an accumulator stage: ONE mbarrier arrival per warp (an arrival is a shared-memory
+// atomic on one address; one per thread and tile would add up)
+__device__ __forceinline__ void release_stage(uint32_t acc_empty) {
+  tc_fence_before();
+  __syncwarp();
+  if ((threadIdx.x & 31) == 0) mbar_arrive_a(acc_empty);
+}
+
+// Max over this thread's row of columns [taddr, taddr + ncols) of one accumulator stage (ncols: multiple of 16, <= 112),
+// then release the stage.  All loads of the half are issued at once (ptxas tracks each LDTM with its own scoreboard,
+// so the FMNMX3s of the first 32 columns run while the rest is still in flight) and the stage goes back to the MMA
+// warp as soon as the last load has landed - before the rest of the fold.
+__device__ __forceinline__ float drain_accumulator(uint32_t taddr, int ncols, uint32_t acc_empty) {
+  Max4 mx;
+  mx.reset();
+  if (ncols == kTN / 2) {  // the full tile: 112 = 32 + 32 + 32 + 16 columns
+    int a[32], b[32], c[32], d[16];
+    tmem_ld32(taddr, a);
+    tmem_ld32(taddr + 32, b);
+    tmem_ld32(taddr + 64, c);
+    tmem_ld16(taddr + 96, d);
+    tmem_ld_wait();
+    release_stage(acc_empty);
+    mx.fold(a);
+    mx.fold(b);
+    mx.fold(c);
+    mx.fold(d);
   } else {  // the last tile of a keyframe: 16 columns at a time
 #pragma unroll 1
-    for (int c = 0; c < ncols; c += 16) {
+    for (int col = 0; col < ncols; col += 16) {
       int v[16];
-      tmem_ld16(taddr + c, v);
+      tmem_ld16(taddr + col, v);
       tmem_ld_wait();
-#pragma unroll
-      for (int j = 0; j < 16; j += 8) {
-        m0 = fmaxf(m0, fmaxf(__int_as_float(v[j + 0]), __int_as_float(v[j + 1])));
-        m1 = fmaxf(m1, fmaxf(__int_as_float(v[j + 2]), __int_as_float(v[j + 3])));
-        m2 = fmaxf(m2, fmaxf(__int_as_float(v[j + 4]), __int_as_float(v[j + 5])));
-        m3 = fmaxf(m3, fmaxf(__int_as_float(v[j + 6]), __int_as_float(v[j + 7])));
-      }
+      mx.fold(v);
     }
+    release_stage(acc_empty);
   }
-  return fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+  return mx.get();
 }
 
 // columns of a tile with `cnt` valid rows: rounded up to 32 (pad rows are copies of the last valid row, so they never
@@ -185,14 +223,17 @@ __global__ void __launch_bounds__(kThreads, 1)
   uint8_t* sB = smem + kOffB;
   float* xch = reinterpret_cast<float*>(smem + kOffXch);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kOffBar);
-  uint64_t* a_full = bars;                          // 1 arrival + tx bytes
-  uint64_t* b_full = bars + 1;                      // [kBStages] one arrival per expander thread
-  uint64_t* b_empty = b_full + kBStages;            // [kBStages] 1 commit
-  uint64_t* acc_full = b_empty + kBStages;          // [kAccStages] 1 commit
-  uint64_t* acc_empty = acc_full + kAccStages;      // [kAccStages] one arrival per epilogue thread
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + kAccStages);
+  // barrier i of a group lives at group base + 8 * i (shared-window addresses)
+  const uint32_t bar0 = smem_u32(bars);
+  const uint32_t a_full = bar0;                               // 1 arrival + tx bytes
+  const uint32_t b_full = bar0 + 8;                           // [kBStages] one arrival per expander warp
+  const uint32_t b_empty = b_full + 8 * kBStages;             // [kBStages] 1 commit
+  const uint32_t acc_full = b_empty + 8 * kBStages;           // [kAccStages] 1 commit
+  const uint32_t acc_empty = acc_full + 8 * kAccStages;       // [kAccStages] one arrival per epilogue warp
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 1 + 2 * kBStages + 2 * kAccStages);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);  // warp-uniform by construction
+  const int lane = threadIdx.x & 31;
   const CtaWork cw = work[blockIdx.x];
   const int slot = cw.slot, n_slots = cw.n_slots;
   const ABlock ab = blocks[cw.ablock];
@@ -202,14 +243,14 @@ __global__ void __launch_bounds__(kThreads, 1)
 
   if (threadIdx.x == 0) {
     if (smem_u32(smem) & 1023u) __trap();
-    mbar_init(a_full, 1);
+    mbar_init(bars, 1);
     for (int i = 0; i < kBStages; ++i) {
-      mbar_init(&b_full[i], kExpWarps * 32);
-      mbar_init(&b_empty[i], 1);
+      mbar_init(bars + 1 + i, kExpWarps);
+      mbar_init(bars + 1 + kBStages + i, 1);
     }
     for (int i = 0; i < kAccStages; ++i) {
-      mbar_init(&acc_full[i], 1);
-      mbar_init(&acc_empty[i], kEpiWarps * 32);
+      mbar_init(bars + 1 + 2 * kBStages + i, 1);
+      mbar_init(bars + 1 + 2 * kBStages + kAccStages + i, kEpiWarps);
     }
     mbar_fence_init();
   }
@@ -231,12 +272,12 @@ __global__ void __launch_bounds__(kThreads, 1)
     // The whole warp runs the (uniform) control flow so descriptors live in uniform registers; one elected lane
     // issues tcgen05.mma / tcgen05.commit.
     if (lane == 0) {
-      mbar_expect_tx(a_full, (uint32_t)m_tiles * kATileBytes);
-      for (int m = 0; m < m_tiles; ++m) bulk_g2s(sA + m * kATileBytes, ab.img + (size_t)m * kATileBytes, kATileBytes, a_full);
+      mbar_expect_tx(bars, (uint32_t)m_tiles * kATileBytes);
+      for (int m = 0; m < m_tiles; ++m) bulk_g2s(sA + m * kATileBytes, ab.img + (size_t)m * kATileBytes, kATileBytes, bars);
     }
     __syncwarp();
     const bool leader = elect_one();
-    mbar_wait_guard(a_full, 0);
+    mbar_wait_a(a_full, 0);
     const uint64_t adesc0 = tc::smem_desc(smem_u32(sA)), bdesc0 = tc::smem_desc(smem_u32(sB));
     const uint32_t sfa = tmem_base + kSfCol, sfb = tmem_base + kSfCol + 8;
     uint32_t par_bfull = 0, n_btiles = 0, t = 0;  // t: accumulator tiles issued so far (stage t & 1)
@@ -247,24 +288,25 @@ __global__ void __launch_bounds__(kThreads, 1)
       for (int row0 = 0; row0 < kf.n; row0 += kTN) {
         const uint32_t idesc = instr_desc_mxf4(tile_cols(min(kTN, kf.n - row0)));
         const uint64_t bdesc = bdesc0 + (uint64_t)((bb * kBTileBytes) >> 4);
-        mbar_wait_guard(&b_full[bb], (par_bfull >> bb) & 1);
+        mbar_wait_a(b_full + 8 * bb, (par_bfull >> bb) & 1);
         par_bfull ^= 1u << bb;
         tc_fence_after();
 #pragma unroll 1
         for (int m = 0; m < m_tiles; ++m, ++t) {
-          mbar_wait_guard(&acc_empty[t & 1], ((t >> 1) & 1) ^ 1);
+          const uint32_t st = t & 1;
+          mbar_wait_a(acc_empty + 8 * st, ((t >> 1) & 1) ^ 1);
           tc_fence_after();
           if (leader) {
-            const uint32_t d = tmem_base + (t & 1) * kAccStride;
+            const uint32_t d = tmem_base + st * kAccStride;
             const uint64_t adesc = adesc0 + (uint64_t)((m * kATileBytes) >> 4);
 #pragma unroll
             for (int s = 0; s < 4; ++s)  // K = 256 = 4 steps of 64 E2M1 values = 32 bytes along the 128-byte row
               umma_mxf4(d, adesc + (uint64_t)(s * 2), bdesc + (uint64_t)(s * 2), idesc, s > 0 ? 1u : 0u, sfa, sfb);
-            umma_commit(&acc_full[t & 1]);
+            umma_commit_a(acc_full + 8 * st);
           }
           __syncwarp();
         }
-        if (leader) umma_commit(&b_empty[bb]);  // arrives when the MMAs reading this B stage have completed
+        if (leader) umma_commit_a(b_empty + 8 * bb);  // arrives when the MMAs reading this B stage have completed
         __syncwarp();
         n_btiles += 1;
         bb = bb + 1 == kBStages ? 0 : bb + 1;
@@ -274,37 +316,45 @@ __global__ void __launch_bounds__(kThreads, 1)
 #pragma unroll
     for (int i = 0; i < kBStages; ++i) {
       const uint32_t n_i = (n_btiles + (kBStages - 1 - i)) / kBStages;  // phases completed on b_empty[i]
-      if (n_i) mbar_wait_guard(&b_empty[i], (n_i - 1) & 1);
+      if (n_i) mbar_wait_a(b_empty + 8 * i, (n_i - 1) & 1);
     }
   } else if (warp >= kEpiWarps) {
     // ===================== B expanders (128 threads) =====================
+    // Thread et owns the descriptor word pair (2 wp, 2 wp + 1) of rows r0 + 32 i, i = 0..6: row & 7 is the same for all
+    // seven, so the swizzled shared-memory offsets and the global offsets differ by constants.
     const int et = threadIdx.x - kEpiWarps * 32;
+    const int r0 = et >> 2, wp = et & 3;
+    const uint32_t off_lo = tile_offset(r0, 2 * wp), off_hi = tile_offset(r0, 2 * wp + 1);
     uint32_t par_bempty = (1u << kBStages) - 1;
     int bb = 0;
     for (int k = k0 + slot; k < k0 + kc; k += n_slots) {
       const KfEntry kf = kfs[k];
       if (!kf_eligible(fr.cur_id, kf.frame_id, kb) || kf.n <= 0) continue;
-      const uint32_t* words = reinterpret_cast<const uint32_t*>(kf.rows);
+      const uint2* pairs = reinterpret_cast<const uint2*>(kf.rows);  // 4 word pairs per 32-byte row
       for (int row0 = 0; row0 < kf.n; row0 += kTN) {
         const int cnt = min(kTN, kf.n - row0);
-        const int nwords = tile_cols(cnt) * 8;
-        uint32_t bits[kWordsPerExpThread];
+        uint2 bits[kPairsPerExpThread];
+        if (cnt == kTN) {  // all loads in flight before the buffer is even free
 #pragma unroll
-        for (int i = 0; i < kWordsPerExpThread; ++i) {  // all loads in flight before the buffer is even free
-          const int idx = et + i * (kExpWarps * 32);
-          const int r = min(idx >> 3, cnt - 1);          // pad rows repeat the last valid row
-          bits[i] = idx < nwords ? __ldg(words + (size_t)(row0 + r) * 8 + (idx & 7)) : 0u;
+          for (int i = 0; i < kPairsPerExpThread; ++i) bits[i] = __ldg(pairs + (size_t)(row0 + r0) * 4 + wp + i * 128);
+        } else {           // last tile: pad rows repeat the last valid row
+#pragma unroll
+          for (int i = 0; i < kPairsPerExpThread; ++i) bits[i] = __ldg(pairs + (size_t)(row0 + min(r0 + 32 * i, cnt - 1)) * 4 + wp);
         }
-        mbar_wait_guard(&b_empty[bb], (par_bempty >> bb) & 1);
+        const int rows_used = tile_cols(cnt);
+        mbar_wait_a(b_empty + 8 * bb, (par_bempty >> bb) & 1);
         par_bempty ^= 1u << bb;
         uint8_t* tile = sB + bb * kBTileBytes;
 #pragma unroll
-        for (int i = 0; i < kWordsPerExpThread; ++i) {
-          const int idx = et + i * (kExpWarps * 32);
-          if (idx < nwords) *reinterpret_cast<uint4*>(tile + tile_offset(idx >> 3, idx & 7)) = expand_word_fp4(bits[i]);
+        for (int i = 0; i < kPairsPerExpThread; ++i) {
+          if (r0 + 32 * i < rows_used) {
+            *reinterpret_cast<uint4*>(tile + off_lo + i * 4096) = expand_word_fp4(bits[i].x);
+            *reinterpret_cast<uint4*>(tile + off_hi + i * 4096) = expand_word_fp4(bits[i].y);
+          }
         }
         fence_proxy_async();  // generic-proxy stores -> visible to the tensor core's async-proxy reads
-        mbar_arrive(&b_full[bb]);
+        __syncwarp();
+        if (lane == 0) mbar_arrive_a(b_full + 8 * bb);
         bb = bb + 1 == kBStages ? 0 : bb + 1;
       }
     }
@@ -312,6 +362,7 @@ __global__ void __launch_bounds__(kThreads, 1)
     // ===================== epilogue (256 threads: warp w owns TMEM lanes 32 (w % 4).., column half w / 4) ====
     const int quad = warp & 3, half = warp >> 2;
     const int row = quad * 32 + lane;  // row inside an A tile
+    const uint32_t tmem_rows = tmem_base + ((uint32_t)(quad * 32) << 16);
     uint32_t t = 0, kpar = 0;
     for (int k = k0 + slot; k < k0 + kc; k += n_slots) {
       const KfEntry kf = kfs[k];
@@ -324,13 +375,10 @@ __global__ void __launch_bounds__(kThreads, 1)
 #pragma unroll
         for (int m = 0; m < kQTilesPerCta; ++m) {
           if (m < m_tiles) {
-            mbar_wait_guard(&acc_full[t & 1], (t >> 1) & 1);
+            const uint32_t st = t & 1;
+            mbar_wait_a(acc_full + 8 * st, (t >> 1) & 1);
             tc_fence_after();
-            const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (t & 1) * kAccStride + (uint32_t)(half * hcols);
-            const float dmax = fold_accumulator(taddr, hcols);  // the TMEM loads have completed when this returns
-            tc_fence_before();
-            mbar_arrive(&acc_empty[t & 1]);  // accumulator stage drained by this thread
-            best[m] = fmaxf(best[m], dmax);
+            best[m] = fmaxf(best[m], drain_accumulator(tmem_rows + st * kAccStride + (uint32_t)(half * hcols), hcols, acc_empty + 8 * st));
             ++t;
           }
         }

@@ -13,7 +13,7 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-fil
   python bench.py --keyframes 6000 --steps 2 --warmup 3 --no-cpu-baseline --no-extra > gpurun_out/${TAG}_ncu1.log 2>&1
 echo "launch list rc=$?"
 python tools/tc_probe.py 0 4000 > gpurun_out/${TAG}_probe.log 2>&1 && \
-ncu --set full --clock-control none --import-source on -k regex:tensor_match -s 3 -c 1 -f -o gpurun_out/${TAG}_tensor \
+ncu --set full --clock-control none --import-source on -k regex:mxf4_match -s 3 -c 1 -f -o gpurun_out/${TAG}_mxf4 \
   python tools/tc_probe.py 0 4000 > gpurun_out/${TAG}_ncu2.log 2>&1
 echo "full capture rc=$?"
 cat gpurun_out/${TAG}_probe.log

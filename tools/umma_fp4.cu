@@ -315,7 +315,9 @@ __global__ void __launch_bounds__(384, 1) both(int N, long long iters, int reade
   } else if (warp >= 4 && readers) {
     const int w = warp - 4, quad = w & 3, half = w >> 2;
     float acc = 0.f;
+    long long nloops = 0;
     while (!done) {
+      ++nloops;
       for (int c = 0; c < 192; c += 64) {
         uint32_t v0[32], v1[32];
         const uint32_t ta = tb + ((uint32_t)(quad * 32) << 16) + (uint32_t)(half * 240 + c);
@@ -327,6 +329,7 @@ __global__ void __launch_bounds__(384, 1) both(int N, long long iters, int reade
       }
     }
     if (acc == 12345.f) sink[threadIdx.x] = 1;
+    if (threadIdx.x == 128) out[148 + blockIdx.x] = nloops;
   }
   asm volatile("tcgen05.fence::before_thread_sync;");
   __syncthreads();
@@ -337,7 +340,7 @@ static int popc32(uint32_t x) { return __builtin_popcount(x); }
 
 int main(int argc, char** argv) {
   const double sustain_s = argc > 1 ? atof(argv[1]) : 1.5;
-  long long* d; CK(cudaMalloc(&d, 148 * 8));
+  long long* d; CK(cudaMalloc(&d, 2 * 148 * 8));
   uint32_t* sink; CK(cudaMalloc(&sink, 4096));
   CK(cudaFuncSetAttribute(correctness, cudaFuncAttributeMaxDynamicSharedMemorySize, 201 * 1024));
   CK(cudaFuncSetAttribute(rate<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 201 * 1024));
@@ -427,7 +430,10 @@ int main(int argc, char** argv) {
       for (int rep = 0; rep < 2; ++rep) { both<<<148, 384, 201 * 1024>>>(N, iters, readers, d, sink); CK(cudaDeviceSynchronize()); }
       CK(cudaMemcpy(h, d, 148 * 8, cudaMemcpyDeviceToHost));
       double mx = 0; for (int i = 0; i < 148; ++i) mx = h[i] > mx ? h[i] : mx;
-      printf("mxf4 N=%3d 2 accumulators, readers=%d: %6.1f cycles/MMA\n", N, readers, mx / (iters * 4));
+      long long h2[148]; CK(cudaMemcpy(h2, d + 148, 148 * 8, cudaMemcpyDeviceToHost));
+      printf("mxf4 N=%3d 2 accumulators, readers=%d: %6.1f cycles/MMA", N, readers, mx / (iters * 4));
+      if (readers) printf("   readers: %.1f B/clk/SM while the MMAs run", (double)h2[0] * 3 * 8 * 2 * 32 * 32 * 4 / (double)h[0]);
+      printf("\n");
     }
   }
 
