@@ -84,9 +84,11 @@ def load():
     """Load liblc_b200.so (building it first if the sources are newer and nvcc is present)."""
     global _lib
     if _lib is None:
-        path = _build.LIB
-        if not os.path.exists(path):
-            path = _build.build()
+        path = os.environ.get("LC_B200_LIB")  # developer knob: A/B another build of the same ABI
+        if not path:
+            path = _build.LIB
+            if not os.path.exists(path):
+                path = _build.build()
         lib = C.CDLL(path)
         for name, (res, args) in SYMBOLS.items():
             fn = getattr(lib, name)  # AttributeError here = the .so does not export the declared ABI

@@ -334,10 +334,12 @@ int run_match(lc_ctx* c, cudaStream_t st, const KfEntry* d_kfs, int n_kf, int ma
         LC_CUDA(c, cudaFuncSetAttribute(fx::mxf4_match_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, fx::kSmemAlloc));
         attr_set = true;
       }
-      const int stride = (max_nq + 3) & ~3;
-      long long kc_max = std::max<long long>(1, (long long)(kScratchBudgetBytes / ((size_t)stride * 4)) / n_frames);
+      // scratch: one distance (mxf4: u16) or key (int8: u32) per (frame, keyframe, query); rows start 16-byte aligned
+      const int stride = (max_nq + 7) & ~7;
+      const size_t elem = want_fp4 ? 2 : 4;
+      long long kc_max = std::max<long long>(1, (long long)(kScratchBudgetBytes / ((size_t)stride * elem)) / n_frames);
       kc_max = std::min<long long>(kc_max, n_kf);
-      LC_TRY(ensure(c, c->d_scratch, (size_t)kc_max * n_frames * stride * 4));
+      LC_TRY(ensure(c, c->d_scratch, (size_t)kc_max * n_frames * stride * elem));
       c->launches += 1;
       c->timing.kernel_launches += 1;
       for (int k0 = 0; k0 < n_kf; k0 += (int)kc_max) {
@@ -345,10 +347,10 @@ int run_match(lc_ctx* c, cudaStream_t st, const KfEntry* d_kfs, int n_kf, int ma
         if (want_fp4) {
           // every compared (frame, keyframe, query) distance is stored exactly once: no scratch initialisation
           fx::mxf4_match_kernel<<<(unsigned)work.size(), fx::kThreads, fx::kSmemAlloc, st>>>(
-              d_kfs, k0, kc, d_frames, (const fx::ABlock*)d_blocks, d_work, (uint32_t*)c->d_scratch.p, stride, kb);
+              d_kfs, k0, kc, d_frames, (const fx::ABlock*)d_blocks, d_work, (uint16_t*)c->d_scratch.p, stride, kb);
           LC_CUDA(c, cudaGetLastError());
-          fx::finalize_dist_kernel<<<kc * n_frames, 256, 0, st>>>(d_kfs, n_kf, k0, kc, d_frames, (const uint32_t*)c->d_scratch.p,
-                                                                 stride, d_results, kb);
+          fx::finalize_dist_kernel<<<(kc * n_frames + fx::kFinWarps - 1) / fx::kFinWarps, fx::kFinWarps * 32, 0, st>>>(
+              d_kfs, n_kf, k0, kc, d_frames, n_frames, (const uint16_t*)c->d_scratch.p, stride, d_results, kb);
         } else {
           LC_CUDA(c, cudaMemsetAsync(c->d_scratch.p, 0xff, (size_t)kc * n_frames * stride * 4, st));
           tc::tensor_match_kernel<<<(unsigned)work.size(), tc::kThreads, tc::kSmemAlloc, st>>>(

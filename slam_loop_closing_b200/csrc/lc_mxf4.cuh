@@ -25,8 +25,9 @@
 //     query with FMNMX3: 448 warp instructions per tile, a quarter of the SM's issue slots - with everything else
 //     the kernel is issue-bound as much as tensor-bound, so per-tile overhead instructions are kept minimal.
 //   * one MMA issuer warp; mbarriers + tcgen05.commit connect the three roles.
-// Output: scratch[(frame * kc + (k - k0)) * stride + q] = min distance, plain stores, every compared (frame, k, q)
-// written exactly once - no memset, no atomics.
+// Output: scratch[(frame * kc + (k - k0)) * stride + q] = min distance (u16), plain stores, every compared (frame, k, q)
+// written exactly once - no memset, no atomics; per query, (min distance << 32 | first keyframe at that distance) is
+// kept in registers over all keyframes of the CTA and folded into best_packed once at the end.
 #pragma once
 #include "lc_tensor.cuh"
 
@@ -216,7 +217,7 @@ __device__ __forceinline__ int tile_cols(int cnt) { return (cnt + 31) & ~31; }
 // One CTA per CtaWork entry: query block `ablock` against keyframes k0 + slot, k0 + slot + n_slots, ...
 __global__ void __launch_bounds__(kThreads, 1)
     mxf4_match_kernel(const KfEntry* __restrict__ kfs, int k0, int kc, const QFrame* __restrict__ frames,
-                      const ABlock* __restrict__ blocks, const CtaWork* __restrict__ work, uint32_t* __restrict__ scratch,
+                      const ABlock* __restrict__ blocks, const CtaWork* __restrict__ work, uint16_t* __restrict__ scratch,
                       int scratch_stride, Knobs kb) {
   extern __shared__ __align__(1024) uint8_t smem[];  // SWIZZLE_128B operands need 1024-byte alignment
   uint8_t* sA = smem;
@@ -224,7 +225,10 @@ __global__ void __launch_bounds__(kThreads, 1)
   float* xch = reinterpret_cast<float*>(smem + kOffXch);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kOffBar);
   // barrier i of a group lives at group base + 8 * i (shared-window addresses)
-  const uint32_t bar0 = smem_u32(bars);
+  // (laundered through an opaque asm: otherwise ptxas rematerialises the address - S2R SR_CgaCtaId + 4 more - on the
+  // critical path of every stage release when registers get tight)
+  uint32_t bar0 = smem_u32(bars);
+  asm volatile("mov.u32 %0, %0;" : "+r"(bar0));
   const uint32_t a_full = bar0;                               // 1 arrival + tx bytes
   const uint32_t b_full = bar0 + 8;                           // [kBStages] one arrival per expander warp
   const uint32_t b_empty = b_full + 8 * kBStages;             // [kBStages] 1 commit
@@ -364,6 +368,11 @@ __global__ void __launch_bounds__(kThreads, 1)
     const int row = quad * 32 + lane;  // row inside an A tile
     const uint32_t tmem_rows = tmem_base + ((uint32_t)(quad * 32) << 16);
     uint32_t t = 0, kpar = 0;
+    // this thread finishes the queries (tile m, row) with m % 2 == half; their running global best (distance, then
+    // lowest keyframe: k only grows, so "<" keeps the first) stays in registers until the CTA is done
+    uint32_t gbest_d[kQTilesPerCta / 2], gbest_k[kQTilesPerCta / 2];
+#pragma unroll
+    for (int j = 0; j < kQTilesPerCta / 2; ++j) gbest_d[j] = 0xffffffffu, gbest_k[j] = 0u;
     for (int k = k0 + slot; k < k0 + kc; k += n_slots) {
       const KfEntry kf = kfs[k];
       if (!kf_eligible(fr.cur_id, kf.frame_id, kb) || kf.n <= 0) continue;
@@ -389,16 +398,27 @@ __global__ void __launch_bounds__(kThreads, 1)
       for (int m = 0; m < kQTilesPerCta; ++m)
         if ((m & 1) != half && m < m_tiles) x[m * kQTile + row] = best[m];
       epi_bar_sync();
-      uint32_t* dst = scratch + ((size_t)ab.frame * kc + (k - k0)) * scratch_stride + ab.q0;
+      uint16_t* dst = scratch + ((size_t)ab.frame * kc + (k - k0)) * scratch_stride + ab.q0;
 #pragma unroll
-      for (int m = 0; m < kQTilesPerCta; ++m) {
-        const int q = m * kQTile + row;
-        if ((m & 1) == half && m < m_tiles && q < nq_blk) {
-          const float d = fmaxf(best[m], x[m * kQTile + row]);  // = 256 - 2 * min hamming
-          dst[q] = (uint32_t)(256 - (int)d) >> 1;
+      for (int j = 0; j < kQTilesPerCta / 2; ++j) {
+        const int m = 2 * j + half, q = m * kQTile + row;
+        if (m < m_tiles && q < nq_blk) {
+          const float mine = half ? best[2 * j + 1] : best[2 * j];  // static register indices
+          const float dot = fmaxf(mine, x[m * kQTile + row]);      // = 256 - 2 * min hamming
+          const uint32_t d = (uint32_t)(256 - (int)dot) >> 1;
+          dst[q] = (uint16_t)d;
+          if (d < gbest_d[j]) gbest_d[j] = d, gbest_k[j] = (uint32_t)k;
         }
       }
       kpar ^= 1;  // the next keyframe writes the other exchange buffer: one barrier per keyframe is enough
+    }
+    if (fr.best_packed) {
+#pragma unroll
+      for (int j = 0; j < kQTilesPerCta / 2; ++j) {
+        const int q = (2 * j + half) * kQTile + row;
+        if (gbest_d[j] != 0xffffffffu)
+          atomicMin((unsigned long long*)(fr.best_packed + ab.q0 + q), ((unsigned long long)gbest_d[j] << 32) | gbest_k[j]);
+      }
     }
   }
   tc_fence_before();
@@ -410,39 +430,71 @@ __global__ void __launch_bounds__(kThreads, 1)
 }
 
 // ---------------------------------------------------------------- finalize (distance-only scratch)
-// one CTA per (frame, keyframe in [k0, k0 + kc)): min distance, 2 x min filter, count -> results[frame * n_kf + k];
-// per query, (dist << 32 | local keyframe index) is folded into best_packed - resolve_best_kernel turns the winning
-// keyframe into the winning row afterwards.
-__global__ void __launch_bounds__(256)
-    finalize_dist_kernel(const KfEntry* __restrict__ kfs, int n_kf, int k0, int kc, const QFrame* __restrict__ frames,
-                         const uint32_t* __restrict__ scratch, int scratch_stride, lc_kf_result* __restrict__ results, Knobs kb) {
-  __shared__ int red[8];
-  const int f = blockIdx.x / kc, k = k0 + (blockIdx.x - f * kc);
+// one WARP per (frame, keyframe in [k0, k0 + kc)): min distance, 2 x min filter, count -> results[frame * n_kf + k].
+// The 16-bit distances of one match (<= 4 KiB) are read once with 128-bit loads and stay in registers for both passes.
+constexpr int kFinWarps = 8;
+constexpr int kFinMaxVec = 16;  // 16 x 32 lanes x 8 distances = 4096 queries per pass
+__global__ void __launch_bounds__(kFinWarps * 32)
+    finalize_dist_kernel(const KfEntry* __restrict__ kfs, int n_kf, int k0, int kc, const QFrame* __restrict__ frames, int n_frames,
+                         const uint16_t* __restrict__ scratch, int scratch_stride, lc_kf_result* __restrict__ results, Knobs kb) {
+  const int lane = threadIdx.x & 31;
+  const int idx = blockIdx.x * kFinWarps + (threadIdx.x >> 5);
+  if (idx >= kc * n_frames) return;
+  const int f = idx / kc, k = k0 + (idx - f * kc);
   const int item = f * n_kf + k;
   const QFrame fr = frames[f];
   const KfEntry kf = kfs[k];
-  const int tid = threadIdx.x;
   if (!kf_eligible(fr.cur_id, kf.frame_id, kb) || kf.n <= 0 || fr.nq <= 0) {
-    if (tid == 0) results[item] = lc_kf_result{kf.frame_id, kf.n, -1, -1};
+    if (lane == 0) results[item] = lc_kf_result{kf.frame_id, kf.n, -1, -1};
     return;
   }
-  const uint32_t* dists = scratch + (size_t)blockIdx.x * scratch_stride;
-  int dmin = 0x7fffffff;
-  for (int i = tid; i < fr.nq; i += blockDim.x) dmin = min(dmin, (int)dists[i]);
-  dmin = block_min(dmin, red);
-  if (kb.min_init >= 0) dmin = min(dmin, kb.min_init);
-  const int thr = filter_threshold(dmin, kb);
-  int cnt_good = 0;
-  for (int i = tid; i < fr.nq; i += blockDim.x) {
-    const uint32_t d = dists[i];
-    cnt_good += is_good((int)d, thr, kb) ? 1 : 0;
-    if (fr.best_packed) {
-      const uint64_t packed = ((uint64_t)d << 32) | (uint32_t)k;
-      if (packed < *(volatile uint64_t*)(fr.best_packed + i)) atomicMin((unsigned long long*)(fr.best_packed + i), (unsigned long long)packed);
+  const uint4* dists = reinterpret_cast<const uint4*>(scratch + (size_t)idx * scratch_stride);
+  int dmin = 0x7fffffff, cnt_good = 0;
+  for (int base = 0; base < fr.nq; base += kFinMaxVec * 256) {  // one pass unless nq > 4096
+    uint4 v[kFinMaxVec];
+    uint32_t mn = 0xffffffffu;
+#pragma unroll
+    for (int i = 0; i < kFinMaxVec; ++i) {
+      const int e = base + (i * 32 + lane) * 8;  // first query of this 128-bit vector
+      v[i] = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
+      if (e < fr.nq) {
+        v[i] = __ldg(dists + (e >> 3));
+        if (e + 8 > fr.nq) {  // the vector straddles nq: entries past it were never written
+          uint32_t w[4] = {v[i].x, v[i].y, v[i].z, v[i].w};
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            if (e + j >= fr.nq) w[j >> 1] |= 0xffffu << (16 * (j & 1));
+          v[i] = make_uint4(w[0], w[1], w[2], w[3]);
+        }
+      }
+      mn = __vminu2(mn, __vminu2(__vminu2(v[i].x, v[i].y), __vminu2(v[i].z, v[i].w)));
+    }
+    if (base == 0 && fr.nq <= kFinMaxVec * 256) {  // the common case: everything is in registers
+      dmin = (int)min(mn & 0xffffu, mn >> 16);
+      dmin = __reduce_min_sync(0xffffffffu, dmin);
+      if (kb.min_init >= 0) dmin = min(dmin, kb.min_init);
+      const int thr = filter_threshold(dmin, kb) - (kb.filter_strict ? 1 : 0);  // good iff d <= thr
+      const uint32_t thr2 = (uint32_t)max(thr, -1) * 0x10001u;                  // thr < 0: nothing passes
+      uint32_t acc = 0;
+      if (thr >= 0) {
+#pragma unroll
+        for (int i = 0; i < kFinMaxVec; ++i)  // __vsetleu2: 1 per 16-bit lane with a <= b
+          acc += __vsetleu2(v[i].x, thr2) + __vsetleu2(v[i].y, thr2) + __vsetleu2(v[i].z, thr2) + __vsetleu2(v[i].w, thr2);
+      }
+      cnt_good = __reduce_add_sync(0xffffffffu, (int)((acc & 0xffffu) + (acc >> 16)));
+    } else {  // nq > 4096: min over all passes first, then a second sweep for the count
+      dmin = min(dmin, (int)min(mn & 0xffffu, mn >> 16));
     }
   }
-  cnt_good = block_sum(cnt_good, red);
-  if (tid == 0) results[item] = lc_kf_result{kf.frame_id, kf.n, dmin, cnt_good};
+  if (fr.nq > kFinMaxVec * 256) {
+    dmin = __reduce_min_sync(0xffffffffu, dmin);
+    if (kb.min_init >= 0) dmin = min(dmin, kb.min_init);
+    const int thr = filter_threshold(dmin, kb);
+    const uint16_t* d16 = scratch + (size_t)idx * scratch_stride;
+    for (int i = lane; i < fr.nq; i += 32) cnt_good += is_good((int)d16[i], thr, kb) ? 1 : 0;
+    cnt_good = __reduce_add_sync(0xffffffffu, cnt_good);
+  }
+  if (lane == 0) results[item] = lc_kf_result{kf.frame_id, kf.n, dmin, cnt_good};
 }
 
 // best_packed[i] = dist << 32 | local keyframe index  ->  dist << 32 | global row of the first row of that keyframe
