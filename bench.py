@@ -11,8 +11,9 @@ all_reduce(MIN) of the packed per-query best and an all_gather of the per-keyfra
             torch's current stream + the collectives), CUDA events, max over ranks.
   e2e     : the same through the host-buffer API (lc_loop_check at N=1, ShardedLoopDB.loop_check at N>1):
             query H2D from pinned memory and records + best D2H inside the timed region.
-  roofline: integer-popc pipe: 148 SM x 16 POPC/clk x f_SM / 8 POPC per pair; the
-            kernel time is liblc_b200's own CUDA-event bracket around its kernels.
+  roofline: tensor bound (the default path is a +/-1 FP4 GEMM on tcgen05: 512 flop per pair) against the measured
+            cuBLAS bf16 peak x 4; the integer-popc roofline of SURVEY.md 8d (148 SM x 16 POPC/clk x f_SM / 8) is kept
+            beside it.  The kernel time is liblc_b200's own CUDA-event bracket around the matching kernel.
   cpu_baseline: cv2.BFMatcher(NORM_HAMMING).match per keyframe + numpy filter (the OpenCV call the
             reference's matcher_ makes), all host threads, on a bounded sample of the same workload.
 
@@ -39,6 +40,10 @@ QUERY_SEED, DB_SEED = 1234, 5678
 CHUNK_KF = 2500  # keyframes generated per device chunk (160 MB)
 POPC_PER_CLK_PER_SM = 16  # measured: profiles/r01_pipe_rates_b200.json (15.1 sustained in a pure-POPC loop)
 POPC_PER_PAIR = 8
+# ncu --set full, lc::fx::mxf4_match_kernel on 4000 keyframes x 2000 rows (profiles/r01_ncu_mxf4_match.txt: 256.6 MB read,
+# 17.7 MB written):
+# dram read + write bytes per keyframe (64,000 B of rows are the algorithmic read; 4,000 B of u16 distances the write)
+TRAFFIC_BYTES_PER_KF = 68_600
 
 WORKLOADS = {
     "c4": dict(keyframes=100_000, name="C4: 2000-descriptor query vs 100k-keyframe DB (200M rows x 256 bit, 6.4 GB)"),
@@ -305,25 +310,33 @@ def main():
 
         step_e2e()
         barrier()
-        kernel_ms = []
+        kernel_ms, match_ms, match_launches = [], [], 1
         t0 = time.perf_counter()
         ev0.record()
         for _ in range(args.steps):
             step_e2e()
             if world == 1:
-                kernel_ms.append(ctx.last_timing().kernel_ms)
+                tm = ctx.last_timing()
+                kernel_ms.append(tm.kernel_ms)
+                match_ms.append(tm.match_ms)
+                match_launches = max(1, tm.match_launches)
         ev1.record()
         barrier()
         e2e_wall_ms = max_over_ranks((time.perf_counter() - t0) * 1e3)
         e2e_ms = max(e2e_wall_ms, max_over_ranks(ev0.elapsed_time(ev1)))
     clocks = clk.summary()
 
-    # ---- dominant-kernel time for the roofline: the library's own event bracket around its kernels
+    # ---- dominant-kernel time for the roofline: CUDA events recorded by the library on its own stream around the
+    #      launches of the matching kernel (lc_timing.match_ms), live, inside the e2e timed region
     if world > 1:
         for _ in range(min(3, args.steps)):
             ctx.loop_check(q, cur_id, want_best=True)
-            kernel_ms.append(ctx.last_timing().kernel_ms)
+            tm = ctx.last_timing()
+            kernel_ms.append(tm.kernel_ms)
+            match_ms.append(tm.match_ms)
+            match_launches = max(1, tm.match_launches)
     k_ms = max_over_ranks(float(np.mean(kernel_ms)))
+    m_ms = max_over_ranks(float(np.mean(match_ms)))
     timing = ctx.last_timing()
 
     if rank != 0:
@@ -334,28 +347,55 @@ def main():
     pk = peaks()
     sm_max = float(pk.get("sm_max_mhz", clocks.get("sm_max_mhz") or 1965.0))
     n_sm = torch.cuda.get_device_properties(device).multi_processor_count
-    peak_pairs = n_sm * POPC_PER_CLK_PER_SM * sm_max * 1e6 / POPC_PER_PAIR / 1e9  # Gpairs/s per GPU
     pairs_per_gpu = pairs_per_step / world
-    ach = pairs_per_gpu / (k_ms * 1e-3) / 1e9
+    kernel_names = {1: "lc::kf_scan_kernel", 2: "lc::split_kernel", 3: "lc::tc::tensor_match_kernel", 4: "lc::fx::mxf4_match_kernel"}
     hbm_peak = float(pk.get("hbm_gbs", 6650.0))
-    algo_bytes = sizes["local_rows"] * 32 + NQ * 32 + sizes["local_keyframes"] * 16 + NQ * 8
-    roof = {
-        "bound": "int_popc", "achieved": ach, "peak": peak_pairs, "unit": "Gpairs/s", "frac": ach / peak_pairs,
-        "traffic": None,
-        "note": f"per GPU; dominant kernel lc::kf_scan_kernel, {k_ms:.2f} ms per launch (library CUDA events); peak = "
-                f"{n_sm} SM x {POPC_PER_CLK_PER_SM} POPC/clk x {sm_max:.0f} MHz / {POPC_PER_PAIR} POPC per pair "
-                f"({'measured' if pk else 'fallback'} sm_max_mhz; POPC rate measured, profiles/r01_pipe_rates_b200.json); "
-                f"the carry-save kernel needs 4 POPC per pair, so frac may exceed 1",
-        "in_kernel_clock_frac": (ach / (peak_pairs * clocks["sm_mhz"] / sm_max)) if clocks.get("sm_mhz") else None,
-        "hbm": {"achieved": algo_bytes / (k_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
-                "frac": algo_bytes / (k_ms * 1e-3) / 1e9 / hbm_peak, "algorithmic_bytes": algo_bytes,
-                "peak_source": "measured" if pk else "fallback"},
-    }
+    algo_bytes = sizes["local_rows"] * 32 + NQ * 32 + sizes["local_keyframes"] * (16 + 2 * NQ) + NQ * 8
+    hbm = {"achieved": algo_bytes / (k_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+           "frac": algo_bytes / (k_ms * 1e-3) / 1e9 / hbm_peak, "algorithmic_bytes": algo_bytes,
+           "peak_source": "measured" if pk else "fallback"}
+    popc_peak = n_sm * POPC_PER_CLK_PER_SM * sm_max * 1e6 / POPC_PER_PAIR / 1e9  # Gpairs/s per GPU
+    pairs_s = pairs_per_gpu / (m_ms * 1e-3)
+    if timing.path in (3, 4):
+        # tensor bound.  Algorithmic work: one pair = a 256-term +/-1 dot product = 256 MAC = 512 flop.
+        # Peak: the driver-measured cuBLAS bf16 figure scaled by the pipe's rate ratio (kind::mxf4 issues 4x, kind::i8
+        # 2x the bf16 MACs per clock: 16384 / 8192 / 4096 MAC/clk/SM) - there is no measured FP4 or int8 entry.
+        ratio, kind = (4.0, "fp4 (kind::mxf4)") if timing.path == 4 else (2.0, "int8 (kind::i8)")
+        bf16 = float(pk.get("bf16_tflops", 1590.0))
+        bf16_sus = float(pk.get("bf16_tflops_sustained", 1400.0))
+        ach = pairs_s * 512 / 1e12
+        mac_clk = 16384 if timing.path == 4 else 8192
+        roof = {
+            "bound": "tensor", "achieved": ach, "peak": ratio * bf16, "unit": "TFLOP/s", "frac": ach / (ratio * bf16),
+            "traffic": TRAFFIC_BYTES_PER_KF * sizes["local_keyframes"] / match_launches,
+            "kernel": kernel_names[timing.path], "ms_per_launch": m_ms / match_launches, "launches_per_step": match_launches,
+            "algorithmic_flop_per_launch": pairs_per_gpu * 512 / match_launches,
+            "peak_source": f"{'measured' if pk else 'fallback'} cuBLAS bf16 burst {bf16:.1f} TFLOP/s x {ratio:.0f} ({kind} MAC rate / bf16 MAC rate); "
+                           f"of {'measured' if pk else 'fallback'}",
+            "frac_of_sustained": ach / (ratio * bf16_sus),
+            "nominal": {"peak": 2250.0 * ratio, "frac": ach / (2250.0 * ratio)},
+            "pipe": {"pairs_per_clk_per_sm": pairs_s / n_sm / ((clocks.get("sm_mhz") or sm_max) * 1e6),
+                     "peak_pairs_per_clk_per_sm": mac_clk / 256, "at_sm_mhz": clocks.get("sm_mhz") or sm_max},
+            "traffic_source": "ncu dram__bytes_read.sum + dram__bytes_write.sum per keyframe of one --set full capture "
+                              "(profiles/), scaled to this launch's keyframes",
+            "note": "per GPU; CUDA events on the library's stream around the matching kernel's launches inside the e2e timed "
+                    "region; a fraction above 1 means the FP4 pipe holds its clock under the power cap better than cuBLAS bf16",
+            "hbm": hbm, "int_popc": {"peak": popc_peak, "unit": "Gpairs/s", "x": pairs_s / 1e9 / popc_peak},
+        }
+    else:
+        ach = pairs_s / 1e9
+        roof = {
+            "bound": "int_popc", "achieved": ach, "peak": popc_peak, "unit": "Gpairs/s", "frac": ach / popc_peak, "traffic": None,
+            "kernel": kernel_names.get(timing.path, "?"), "ms_per_launch": m_ms / match_launches,
+            "note": f"per GPU; integer kernels (neither HBM nor tensor bounds them): peak = {n_sm} SM x {POPC_PER_CLK_PER_SM} POPC/clk x "
+                    f"{sm_max:.0f} MHz / {POPC_PER_PAIR} POPC per pair; the carry-save kernel needs 4 POPC per pair, so frac may exceed 1",
+            "hbm": hbm,
+        }
     line = {
         "metric": "Gpairs/s 256-bit Hamming BF match (loop check vs keyframe DB)",
         "value": pairs_per_step * args.steps / (dev_ms * 1e-3) / 1e9, "unit": "Gpairs/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
-        "scaling": "strong", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
+        "scaling": "strong", "vs_baseline": None, "dtype": {4: "fp4", 3: "s8"}.get(timing.path, "u32"), "data": "synthetic",
         "config": {"workload": wl["name"] if not args.keyframes else f"{n_kf}-keyframe DB x {ROWS_PER_KF} rows", "keyframes": n_kf,
                    "rows_per_keyframe": ROWS_PER_KF, "nq": NQ, "pairs_per_step": pairs_per_step,
                    "sharding": f"keyframe k -> rank k % {world}; NCCL all_reduce(MIN) u64 + all_gather per step" if world > 1 else "single GPU",

@@ -31,7 +31,7 @@ class Config(C.Structure):
 
 class Timing(C.Structure):
     _fields_ = [("h2d_ms", C.c_float), ("kernel_ms", C.c_float), ("d2h_ms", C.c_float), ("total_ms", C.c_float),
-                ("kernel_launches", C.c_int32), ("path", C.c_int32)]
+                ("kernel_launches", C.c_int32), ("path", C.c_int32), ("match_ms", C.c_float), ("match_launches", C.c_int32)]
 
 
 class LcError(RuntimeError):

@@ -69,6 +69,10 @@ struct lc_ctx {
 
   lc_timing timing{};
   int64_t launches = 0;
+  // event pairs around the launches of the matching kernel of the current host-buffer call (lc_timing.match_ms)
+  std::vector<cudaEvent_t> match_ev;
+  size_t match_ev_used = 0;
+  bool timing_on = false;
 };
 
 namespace {
@@ -126,6 +130,28 @@ int ensure_pin_down(lc_ctx* c, size_t bytes) {
   c->pin_down_cap = ncap;
   return LC_OK;
 }
+
+// bracket the launches of the matching kernel with events while a host-buffer call is being timed
+struct MatchTimer {
+  lc_ctx* c;
+  cudaStream_t st;
+  bool on;
+  MatchTimer(lc_ctx* ctx, cudaStream_t s) : c(ctx), st(s), on(ctx->timing_on && s == ctx->stream) {
+    if (!on) return;
+    if (c->match_ev_used + 2 > c->match_ev.size()) {
+      cudaEvent_t a = nullptr, b = nullptr;
+      if (cudaEventCreate(&a) != cudaSuccess || cudaEventCreate(&b) != cudaSuccess) { on = false; return; }
+      c->match_ev.push_back(a);
+      c->match_ev.push_back(b);
+    }
+    cudaEventRecord(c->match_ev[c->match_ev_used], st);
+  }
+  ~MatchTimer() {
+    if (!on) return;
+    cudaEventRecord(c->match_ev[c->match_ev_used + 1], st);
+    c->match_ev_used += 2;
+  }
+};
 
 Knobs knobs_of(const lc_config& g) {
   return Knobs{g.min_loop_gap, g.gap_strict, g.filter_floor, g.filter_strict, g.min_init, 1u << kKeyShift};
@@ -346,15 +372,21 @@ int run_match(lc_ctx* c, cudaStream_t st, const KfEntry* d_kfs, int n_kf, int ma
         const int kc = (int)std::min<long long>(kc_max, n_kf - k0);
         if (want_fp4) {
           // every compared (frame, keyframe, query) distance is stored exactly once: no scratch initialisation
-          fx::mxf4_match_kernel<<<(unsigned)work.size(), fx::kThreads, fx::kSmemAlloc, st>>>(
-              d_kfs, k0, kc, d_frames, (const fx::ABlock*)d_blocks, d_work, (uint16_t*)c->d_scratch.p, stride, kb);
+          {
+            MatchTimer mt(c, st);
+            fx::mxf4_match_kernel<<<(unsigned)work.size(), fx::kThreads, fx::kSmemAlloc, st>>>(
+                d_kfs, k0, kc, d_frames, (const fx::ABlock*)d_blocks, d_work, (uint16_t*)c->d_scratch.p, stride, kb);
+          }
           LC_CUDA(c, cudaGetLastError());
           fx::finalize_dist_kernel<<<(kc * n_frames + fx::kFinWarps - 1) / fx::kFinWarps, fx::kFinWarps * 32, 0, st>>>(
               d_kfs, n_kf, k0, kc, d_frames, n_frames, (const uint16_t*)c->d_scratch.p, stride, d_results, kb);
         } else {
           LC_CUDA(c, cudaMemsetAsync(c->d_scratch.p, 0xff, (size_t)kc * n_frames * stride * 4, st));
-          tc::tensor_match_kernel<<<(unsigned)work.size(), tc::kThreads, tc::kSmemAlloc, st>>>(
-              d_kfs, k0, kc, d_frames, d_blocks, d_work, (uint32_t*)c->d_scratch.p, stride, kb);
+          {
+            MatchTimer mt(c, st);
+            tc::tensor_match_kernel<<<(unsigned)work.size(), tc::kThreads, tc::kSmemAlloc, st>>>(
+                d_kfs, k0, kc, d_frames, d_blocks, d_work, (uint32_t*)c->d_scratch.p, stride, kb);
+          }
           LC_CUDA(c, cudaGetLastError());
           finalize_kernel<<<kc * n_frames, 256, 0, st>>>(d_kfs, n_kf, k0, kc, d_frames, (const uint32_t*)c->d_scratch.p, stride,
                                                          d_results, po.train_idx, po.dist, po.good, po.summary, kb);
@@ -392,6 +424,7 @@ int run_match(lc_ctx* c, cudaStream_t st, const KfEntry* d_kfs, int n_kf, int ma
       LC_TRY(ensure(c, c->d_counter, 256));
       LC_CUDA(c, cudaMemsetAsync(c->d_counter.p, 0, sizeof(int), st));
       const dim3 grid((unsigned)std::min<long long>(slots, n_items));
+      MatchTimer mt(c, st);
       cudaError_t e = mode == MODE_POPC
                           ? launch_scan_m<MODE_POPC>(sh.rq, grid, sh.threads, st, d_kfs, n_kf, d_frames, n_frames, d_results, (int*)c->d_counter.p, kb)
                           : launch_scan_m<MODE_CSA>(sh.rq, grid, sh.threads, st, d_kfs, n_kf, d_frames, n_frames, d_results, (int*)c->d_counter.p, kb);
@@ -431,6 +464,7 @@ int run_match(lc_ctx* c, cudaStream_t st, const KfEntry* d_kfs, int n_kf, int ma
     LC_CUDA(c, cudaMemsetAsync(c->d_scratch.p, 0xff, (size_t)nb * stride * 4, st));
     if (max_rows > 0) {
       const dim3 grid(n_seg, nb, sh.chunks);
+      MatchTimer mt(c, st);
       cudaError_t e = mode == MODE_POPC
                           ? launch_split_m<MODE_POPC>(sh.rq, grid, sh.threads, st, d_kfs, k0, kc, d_frames, (uint32_t*)c->d_scratch.p, stride, seg, kb)
                           : launch_split_m<MODE_CSA>(sh.rq, grid, sh.threads, st, d_kfs, k0, kc, d_frames, (uint32_t*)c->d_scratch.p, stride, seg, kb);
@@ -508,6 +542,8 @@ int stage_query(lc_ctx* c, DevBuf& buf, const uint8_t* q, int64_t n, size_t stri
 
 void timing_begin(lc_ctx* c) {
   c->timing = lc_timing{};
+  c->match_ev_used = 0;
+  c->timing_on = true;
   cudaEventRecord(c->ev[0], c->stream);
 }
 int timing_end(lc_ctx* c) {
@@ -517,6 +553,14 @@ int timing_end(lc_ctx* c) {
   cudaEventElapsedTime(&c->timing.kernel_ms, c->ev[1], c->ev[2]);
   cudaEventElapsedTime(&c->timing.d2h_ms, c->ev[2], c->ev[3]);
   cudaEventElapsedTime(&c->timing.total_ms, c->ev[0], c->ev[3]);
+  c->timing_on = false;
+  for (size_t i = 0; i + 1 < c->match_ev_used; i += 2) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, c->match_ev[i], c->match_ev[i + 1]) == cudaSuccess) {
+      c->timing.match_ms += ms;
+      c->timing.match_launches += 1;
+    }
+  }
   return LC_OK;
 }
 
@@ -604,6 +648,7 @@ LC_API void lc_destroy(lc_ctx* c) {
   if (c->pin_down) cudaFreeHost(c->pin_down);
   for (auto& e : c->ev) if (e) cudaEventDestroy(e);
   for (auto& e : c->pin_ev) if (e) cudaEventDestroy(e);
+  for (auto& e : c->match_ev) if (e) cudaEventDestroy(e);
   if (c->stream) cudaStreamDestroy(c->stream);
   delete c;
 }
@@ -903,6 +948,7 @@ LC_API int32_t lc_match_pair_device(lc_ctx* c, const void* d_q, int32_t nq, cons
   if (((uintptr_t)d_q | (uintptr_t)d_t) % 16 != 0) return fail(c, LC_ERR_INVALID, "device rows must be 16-byte aligned");
   LC_CUDA(c, cudaSetDevice(c->cfg.device));
   cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : c->stream;
+  c->timing_on = false;  // asynchronous entry point: nothing is timed
   if (nq == 0 || nt == 0) {
     if (d_summary) {
       const int32_t s[2] = {-1, 0};
@@ -924,6 +970,7 @@ LC_API int32_t lc_loop_check_batch_device(lc_ctx* c, int32_t n_frames, const voi
   if (!d_results && !c->h_kf.empty() && n_frames > 0) return fail(c, LC_ERR_INVALID, "d_results is NULL");
   LC_CUDA(c, cudaSetDevice(c->cfg.device));
   cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : c->stream;
+  c->timing_on = false;  // asynchronous entry point: nothing is timed
   return loop_check_device_impl(c, st, n_frames, d_q, nq, cur_ids, d_results, d_best);
   LC_GUARD_END(c)
 }

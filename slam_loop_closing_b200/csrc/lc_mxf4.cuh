@@ -513,16 +513,22 @@ __global__ void __launch_bounds__(256)
       const KfEntry kf = kfs[(uint32_t)packed];
       const uint4 qa = __ldg(fr.q + 2 * (size_t)i), qb = __ldg(fr.q + 2 * (size_t)i + 1);
       int found = -1;
-      for (int j0 = 0; j0 < kf.n && found < 0; j0 += 32) {
-        const int j = j0 + lane;
-        int dj = -1;
-        if (j < kf.n) {
-          const uint4 a = __ldg(kf.rows + 2 * (size_t)j), b = __ldg(kf.rows + 2 * (size_t)j + 1);
-          dj = __popc(qa.x ^ a.x) + __popc(qa.y ^ a.y) + __popc(qa.z ^ a.z) + __popc(qa.w ^ a.w) + __popc(qb.x ^ b.x) +
-               __popc(qb.y ^ b.y) + __popc(qb.z ^ b.z) + __popc(qb.w ^ b.w);
+      for (int j0 = 0; j0 < kf.n && found < 0; j0 += 128) {  // four independent 32-row groups in flight per step
+        uint32_t hit[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int j = j0 + 32 * u + lane;
+          int dj = -1;
+          if (j < kf.n) {
+            const uint4 a = __ldg(kf.rows + 2 * (size_t)j), b = __ldg(kf.rows + 2 * (size_t)j + 1);
+            dj = __popc(qa.x ^ a.x) + __popc(qa.y ^ a.y) + __popc(qa.z ^ a.z) + __popc(qa.w ^ a.w) + __popc(qb.x ^ b.x) +
+                 __popc(qb.y ^ b.y) + __popc(qb.z ^ b.z) + __popc(qb.w ^ b.w);
+          }
+          hit[u] = __ballot_sync(0xffffffffu, dj == d);
         }
-        const uint32_t hit = __ballot_sync(0xffffffffu, dj == d);
-        if (hit) found = j0 + __ffs(hit) - 1;
+#pragma unroll
+        for (int u = 3; u >= 0; --u)
+          if (hit[u]) found = j0 + 32 * u + __ffs(hit[u]) - 1;  // the lowest group wins
       }
       if (found < 0) __trap();  // the distance came from this keyframe: a miss is a kernel bug
       if (lane == 0) fr.best_packed[i] = ((uint64_t)d << 32) | (uint64_t)(kf.global_row_off + found);

@@ -22,6 +22,7 @@ import torch.distributed as dist
 from . import _native
 
 _SENTINEL = (-1, 0, -1, -1)  # padding record for ranks with one keyframe fewer
+_SIGN = -(1 << 63)
 
 
 class NativeShard:
@@ -30,6 +31,8 @@ class NativeShard:
     def __init__(self, rank, world, device, **cfg):
         self.device = torch.device("cuda", device)
         self.ctx = _native.Context(device=device, shard_rank=rank, shard_world=world, **cfg)
+        self._sentinel = torch.tensor(_SENTINEL, dtype=torch.int32, device=self.device)
+        self._pin = None  # pinned staging for host queries, grown on demand
 
     def append(self, frame_id, desc, n):
         if desc is None:
@@ -42,16 +45,25 @@ class NativeShard:
 
     def to_device(self, q_rows: np.ndarray) -> torch.Tensor:
         t = torch.from_numpy(np.ascontiguousarray(q_rows, np.uint8).reshape(-1, 32))
-        return t.pin_memory().to(self.device, non_blocking=True) if t.numel() else t.to(self.device)
+        if not t.numel():
+            return t.to(self.device)
+        if self._pin is None or self._pin.shape[0] < t.shape[0]:
+            self._pin = torch.empty((max(t.shape[0], 4096), 32), dtype=torch.uint8).pin_memory()
+        else:
+            torch.cuda.current_stream(self.device).synchronize()  # the previous upload has left the staging buffer
+        self._pin[:t.shape[0]].copy_(t)
+        return self._pin[:t.shape[0]].to(self.device, non_blocking=True)
 
     def loop_check(self, d_q: torch.Tensor, nq, cur_ids, slots):
         """d_q: (sum nq, 32) uint8 CUDA tensor.  Returns (records int32 [F, slots, 4], best int64 [sum nq])."""
         F = len(nq)
         rec = torch.empty((F, slots, 4), dtype=torch.int32, device=self.device)
-        rec[:] = torch.tensor(_SENTINEL, dtype=torch.int32, device=self.device)
         nloc = self.local_keyframes()
+        if nloc != slots:
+            rec[:, nloc:] = self._sentinel  # this rank holds one keyframe fewer: pad
         best = torch.empty(int(np.sum(nq)), dtype=torch.int64, device=self.device)
-        local = torch.empty((F, nloc, 4), dtype=torch.int32, device=self.device) if nloc != slots else rec
+        # one frame: the library's [nloc] records are a prefix of rec[0]; several: it writes [F, nloc] contiguously
+        local = torch.empty((F, nloc, 4), dtype=torch.int32, device=self.device) if (nloc != slots and F > 1) else rec
         # NULL means "the context's own stream" in the C ABI; torch's default stream is handle 0, so name it
         # explicitly (cudaStreamLegacy == 0x1) to stay ordered with the torch ops around this call
         stream = torch.cuda.current_stream(self.device).cuda_stream or 1
@@ -120,8 +132,11 @@ class ShardedLoopDB:
         if self.world == 1:
             return rec, best
         if best.numel():
-            # dist <= 256 keeps the packed value positive, so the signed int64 min is the uint64 min
+            # the packed values are uint64 (UINT64_MAX = "nothing compared on this shard") carried in int64 tensors:
+            # flipping the sign bit makes the signed MIN the collectives offer the unsigned min
+            best ^= _SIGN
             dist.all_reduce(best, op=dist.ReduceOp.MIN, group=self.group)
+            best ^= _SIGN
         F = rec.shape[0]
         gathered = torch.empty((self.world * F, slots, 4), dtype=rec.dtype, device=rec.device)
         dist.all_gather_into_tensor(gathered, rec.contiguous(), group=self.group)

@@ -63,8 +63,9 @@ class OracleShard:
 
 def _case():
     q0 = datagen.low_entropy(150, 1)  # ties that straddle shards
-    qs = [q0, datagen.low_entropy(90, 2), np.zeros((0, 32), np.uint8)]
-    curs = [40, 25, 40]
+    # the last query sees keyframes 0 and 1 only: with 3 ranks one shard compares nothing and reports UINT64_MAX
+    qs = [q0, datagen.low_entropy(90, 2), np.zeros((0, 32), np.uint8), datagen.low_entropy(70, 4)]
+    curs = [40, 25, 40, 6]
     ns = np.random.default_rng(3).integers(0, 60, 23)
     kfs = [datagen.low_entropy(int(n), 100 + i) for i, n in enumerate(ns)]
     return qs, curs, kfs, list(range(len(kfs))), Params(min_loop_gap=5, loop_threshold=0.15)
