@@ -46,7 +46,7 @@ def test_tensor_query_sizes_low_entropy_ties(lc, kernel, nq):
         _check(c, q, kfs, list(range(300)), 1000, p, kernel)
 
 
-@pytest.mark.parametrize("rows", [1, 15, 16, 17, 31, 33, 191, 192, 193, 223, 224, 225, 383, 384, 385, 447, 448, 449, 2000])
+@pytest.mark.parametrize("rows", [1, 15, 16, 17, 31, 33, 127, 128, 129, 191, 192, 193, 223, 224, 225, 255, 256, 257, 383, 384, 385, 2000])
 @pytest.mark.parametrize("kernel", KERNELS)
 def test_tensor_keyframe_row_counts(lc, kernel, rows):
     """train rows around the 16-row MMA N granule and the 192-row B tile."""

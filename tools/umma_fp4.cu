@@ -159,11 +159,16 @@ __global__ void __launch_bounds__(128, 1) correctness(const uint32_t* qbits, con
 // KIND 0 = i8 (K = 32 elements = 32 B per MMA), 1 = mxf4 (K = 64 elements = 32 B per MMA).  Each iteration issues
 // `per_tile` MMAs into accumulator (it % n_acc); operands are random +/-1 images already in shared memory.
 template <int KIND>
-__global__ void __launch_bounds__(128, 1) rate(int N, long long iters, int n_acc, int per_tile, long long* out) {
+__global__ void __launch_bounds__(128, 1) rate(int N, long long iters, int n_acc, int per_tile, long long* out, int commit_each = 0) {
   extern __shared__ uint8_t raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)raw + 1023) & ~(uintptr_t)1023);
   __shared__ uint64_t bar;
+  __shared__ uint64_t bar2[2];
   __shared__ uint32_t tslot;
+  if (threadIdx.x == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar2[0])));
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar2[1])));
+  }
   uint32_t rng = 0x9e3779b9u * (blockIdx.x * 128 + threadIdx.x + 1);
   for (int i = threadIdx.x; i < kSmemOps / 4; i += blockDim.x) {
     rng = rng * 1664525u + 1013904223u;
@@ -211,6 +216,7 @@ __global__ void __launch_bounds__(128, 1) rate(int N, long long iters, int n_acc
           if (KIND == 0) umma_i8(d, da + (ka >> 4), db + (kb >> 4), idesc, s > 0);
           else umma_mxf4(d, da + (ka >> 4), db + (kb >> 4), idesc, s > 0, tb + kSfCol, tb + kSfCol + 32);
         }
+        if (commit_each) commit(&bar2[it & 1]);
       }
       __syncwarp();
     }
@@ -336,16 +342,234 @@ __global__ void __launch_bounds__(384, 1) both(int N, long long iters, int reade
   if (threadIdx.x < 32) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tb), "r"(512u));
 }
 
+// two issuer warps taking turns tile by tile (4 MMAs + commit each); a named barrier hands the turn over right after the
+// fourth MMA, so one warp's commit overlaps the other warp's MMA issue
+__global__ void __launch_bounds__(128, 1) rate2(int N, int iters, long long* out, int handoff_before_commit) {
+  extern __shared__ uint8_t raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)raw + 1023) & ~(uintptr_t)1023);
+  __shared__ uint64_t bar[2];
+  __shared__ uint32_t tslot;
+  uint32_t rng = 0x9e3779b9u * (blockIdx.x * 128 + threadIdx.x + 1);
+  for (int i = threadIdx.x; i < kSmemOps / 4; i += blockDim.x) {
+    rng = rng * 1664525u + 1013904223u;
+    ((uint32_t*)smem)[i] = expand8_fp4((rng >> 8) & 255u);
+  }
+  if (threadIdx.x == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar[0])));
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar[1])));
+    asm volatile("fence.mbarrier_init.release.cluster;");
+  }
+  if (threadIdx.x < 32) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tslot)), "r"(512u));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  asm volatile("fence.proxy.async.shared::cta;");
+  asm volatile("tcgen05.fence::before_thread_sync;");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;");
+  const uint32_t tb = tslot;
+  const int warp = threadIdx.x >> 5;
+  for (int c = 0; c < 32; ++c) tmem_st1(tb + ((uint32_t)(warp * 32) << 16) + 480 + c, 0x7f7f7f7fu);
+  asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+  asm volatile("tcgen05.fence::before_thread_sync;");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;");
+  if (warp < 2) {
+    const uint32_t idesc = idesc_mxf4(N, 0, 0);
+    const uint64_t da = smem_desc(smem_u32(smem)), db = smem_desc(smem_u32(smem) + 64 * 1024);
+    uint32_t el;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(el));
+    const uint32_t d = tb + (uint32_t)warp * 240;
+    long long t0 = clock64();
+    if (warp == 1) asm volatile("bar.sync 3, 64;" ::: "memory");  // wait for warp 0's first turn
+    for (int it = 0; it < iters; ++it) {
+      if (el)
+        for (int s = 0; s < 4; ++s) umma_mxf4(d, da + (uint64_t)((s * 32) >> 4), db + (uint64_t)((s * 32) >> 4), idesc, s > 0, tb + 480, tb + 496);
+      __syncwarp();
+      if (handoff_before_commit) {
+        asm volatile("bar.arrive %0, 64;" ::"r"(2 + (warp ^ 1)) : "memory");   // the other warp may go
+        if (el) commit(&bar[warp]);
+      } else {
+        if (el) commit(&bar[warp]);
+        asm volatile("bar.arrive %0, 64;" ::"r"(2 + (warp ^ 1)) : "memory");
+      }
+      __syncwarp();
+      if (it + 1 < iters || warp == 0) asm volatile("bar.sync %0, 64;" ::"r"(2 + warp) : "memory");  // my next turn
+    }
+    // wait for my last commit
+    wait_bar(&bar[warp], (iters - 1) & 1);
+    long long t1 = clock64();
+    if (threadIdx.x == 32) out[blockIdx.x] = t1 - t0;
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;");
+  __syncthreads();
+  if (threadIdx.x < 32) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tb), "r"(512u));
+}
+
+// pure TMEM read bandwidth: `nwarps` warps, each issuing `depth` x32 loads back to back before one wait (no math),
+// optionally while warp 0 keeps the tensor pipe busy
+template <int DEPTH>
+__global__ void __launch_bounds__(544, 1) tmem_bw(int iters, int nwarps, int with_mma, long long* out, uint32_t* sink, int mode = 0) {
+  extern __shared__ uint8_t raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)raw + 1023) & ~(uintptr_t)1023);
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tslot;
+  __shared__ int done;  // reader warps that have finished
+  for (int i = threadIdx.x; i < kSmemOps / 4; i += blockDim.x) ((uint32_t*)smem)[i] = expand8_fp4((i * 2654435761u >> 8) & 255u);
+  if (threadIdx.x == 0) {
+    done = 0;
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar)));
+    asm volatile("fence.mbarrier_init.release.cluster;");
+  }
+  if (threadIdx.x < 32) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tslot)), "r"(512u));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  asm volatile("fence.proxy.async.shared::cta;");
+  asm volatile("tcgen05.fence::before_thread_sync;");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;");
+  const uint32_t tb = tslot;
+  const int warp = threadIdx.x >> 5;
+  if (warp < 4) {
+    for (int c = 0; c < 32; ++c) tmem_st1(tb + ((uint32_t)(warp * 32) << 16) + 480 + c, 0x7f7f7f7fu);
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;");
+  if (warp == 0) {
+    if (with_mma) {
+      const uint32_t idesc = idesc_mxf4(224, 0, 0);
+      const uint64_t da = smem_desc(smem_u32(smem)), db = smem_desc(smem_u32(smem) + 64 * 1024);
+      uint32_t el;
+      asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(el));
+      long long it = 0;
+      const long long m0 = clock64();
+      while (*(volatile int*)&done < nwarps && it < (1ll << 22)) {  // bounded: a protocol slip must not hang the GPU
+        const uint32_t d = tb + (uint32_t)(it++ & 1) * 240;
+        if (el)
+          for (int s = 0; s < 4; ++s) umma_mxf4(d, da + (uint64_t)((s * 32) >> 4), db + (uint64_t)((s * 32) >> 4), idesc, s > 0, tb + 480, tb + 496);
+        __syncwarp();
+      }
+      if (el) commit(&bar);
+      __syncwarp();
+      wait_bar(&bar, 0);
+      if (threadIdx.x == 0) { out[148 * 16 + blockIdx.x * 2] = clock64() - m0; out[148 * 16 + blockIdx.x * 2 + 1] = it * 4; }
+    }
+  } else if (warp <= nwarps) {
+    const int w = warp - 1, quad = warp & 3;
+    uint32_t acc = 0;
+    long long t0 = clock64();
+    for (int it = 0; it < iters; ++it) {
+      uint32_t v[DEPTH][32];
+#pragma unroll
+      for (int k = 0; k < DEPTH; ++k) tmem_ld32(tb + ((uint32_t)(quad * 32) << 16) + (uint32_t)(((w >> 2) * 32 * DEPTH + k * 32 + it * 64) & 255), v[k]);
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      if (mode & 1) {
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncwarp();
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      }
+      if (mode & 2) {
+        float m0 = -1e30f, m1 = -1e30f, m2 = -1e30f, m3 = -1e30f;
+#pragma unroll
+        for (int k = 0; k < DEPTH; ++k)
+#pragma unroll
+          for (int j = 0; j < 32; j += 8) {
+            m0 = fmaxf(m0, fmaxf(__uint_as_float(v[k][j]), __uint_as_float(v[k][j + 1])));
+            m1 = fmaxf(m1, fmaxf(__uint_as_float(v[k][j + 2]), __uint_as_float(v[k][j + 3])));
+            m2 = fmaxf(m2, fmaxf(__uint_as_float(v[k][j + 4]), __uint_as_float(v[k][j + 5])));
+            m3 = fmaxf(m3, fmaxf(__uint_as_float(v[k][j + 6]), __uint_as_float(v[k][j + 7])));
+          }
+        acc ^= __float_as_uint(fmaxf(fmaxf(m0, m1), fmaxf(m2, m3)));
+      } else {
+#pragma unroll
+        for (int k = 0; k < DEPTH; ++k) acc ^= v[k][0] ^ v[k][31];
+      }
+    }
+    long long t1 = clock64();
+    if ((threadIdx.x & 31) == 0) { out[blockIdx.x * 16 + w] = t1 - t0; atomicAdd(&done, 1); }
+    if (acc == 0x12345u) sink[threadIdx.x] = acc;
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;");
+  __syncthreads();
+  if (threadIdx.x < 32) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tb), "r"(512u));
+}
+
+// MMA rate (warp 0, N = 224, alternating accumulators) while `npoll` other warps spin on mbarrier.try_wait of a phase that
+// never completes: does barrier polling steal shared-memory bandwidth from the tensor core's operand fetch?
+__global__ void __launch_bounds__(544, 1) poll_vs_mma(int iters, int npoll, int sleep_ns, long long* out) {
+  extern __shared__ uint8_t raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)raw + 1023) & ~(uintptr_t)1023);
+  __shared__ uint64_t bar, never;
+  __shared__ uint32_t tslot;
+  __shared__ int done;
+  for (int i = threadIdx.x; i < kSmemOps / 4; i += blockDim.x) ((uint32_t*)smem)[i] = expand8_fp4((i * 2654435761u >> 8) & 255u);
+  if (threadIdx.x == 0) {
+    done = 0;
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar)));
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&never)));
+    asm volatile("fence.mbarrier_init.release.cluster;");
+  }
+  if (threadIdx.x < 32) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tslot)), "r"(512u));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  asm volatile("fence.proxy.async.shared::cta;");
+  asm volatile("tcgen05.fence::before_thread_sync;");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;");
+  const uint32_t tb = tslot;
+  const int warp = threadIdx.x >> 5;
+  if (warp < 4) {
+    for (int c = 0; c < 32; ++c) tmem_st1(tb + ((uint32_t)(warp * 32) << 16) + 480 + c, 0x7f7f7f7fu);
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;");
+  if (warp == 0) {
+    const uint32_t idesc = idesc_mxf4(224, 0, 0);
+    const uint64_t da = smem_desc(smem_u32(smem)), db = smem_desc(smem_u32(smem) + 64 * 1024);
+    uint32_t el;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(el));
+    const long long t0 = clock64();
+    for (int it = 0; it < iters; ++it) {
+      const uint32_t d = tb + (uint32_t)(it & 1) * 240;
+      if (el)
+        for (int s = 0; s < 4; ++s) umma_mxf4(d, da + (uint64_t)((s * 32) >> 4), db + (uint64_t)((s * 32) >> 4), idesc, s > 0, tb + 480, tb + 496);
+      __syncwarp();
+    }
+    if (el) commit(&bar);
+    __syncwarp();
+    wait_bar(&bar, 0);
+    if (threadIdx.x == 0) { out[blockIdx.x] = clock64() - t0; *(volatile int*)&done = 1; }
+  } else if (warp <= npoll) {
+    long long guard = 0;
+    while (!*(volatile int*)&done && guard++ < (1ll << 24)) {
+      uint32_t ok;
+      asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(smem_u32(&never)), "r"(0u) : "memory");
+      if (sleep_ns) __nanosleep(sleep_ns);
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;");
+  __syncthreads();
+  if (threadIdx.x < 32) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tb), "r"(512u));
+}
+
 static int popc32(uint32_t x) { return __builtin_popcount(x); }
 
 int main(int argc, char** argv) {
+  setvbuf(stdout, nullptr, _IOLBF, 0);
   const double sustain_s = argc > 1 ? atof(argv[1]) : 1.5;
-  long long* d; CK(cudaMalloc(&d, 2 * 148 * 8));
+  long long* d; CK(cudaMalloc(&d, 20 * 148 * 8));
   uint32_t* sink; CK(cudaMalloc(&sink, 4096));
   CK(cudaFuncSetAttribute(correctness, cudaFuncAttributeMaxDynamicSharedMemorySize, 201 * 1024));
   CK(cudaFuncSetAttribute(rate<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 201 * 1024));
   CK(cudaFuncSetAttribute(rate<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 201 * 1024));
   CK(cudaFuncSetAttribute(both, cudaFuncAttributeMaxDynamicSharedMemorySize, 201 * 1024));
+  CK(cudaFuncSetAttribute(rate2, cudaFuncAttributeMaxDynamicSharedMemorySize, 201 * 1024));
 
   // ---- 1. correctness
   for (int N : {128, 256}) {
@@ -423,6 +647,29 @@ int main(int argc, char** argv) {
     const double per = mx / (iters * 4);
     printf("mxf4 N=%3d: %6.1f cycles/MMA (floor %5.1f)  %6.0f MAC/clk/SM\n", N, per, N / 2.0, 128.0 * N * 64 / per);
   }
+  // ---- 2b'. one commit per tile (4 MMAs) into alternating accumulators
+  for (int ce : {0, 1}) {
+    const long long iters = 4096;
+    for (int rep = 0; rep < 2; ++rep) { rate<1><<<148, 128, 201 * 1024>>>(224, iters, 2, 4, d, ce); CK(cudaDeviceSynchronize()); }
+    CK(cudaMemcpy(h, d, 148 * 8, cudaMemcpyDeviceToHost));
+    double mx = 0; for (int i = 0; i < 148; ++i) mx = h[i] > mx ? h[i] : mx;
+    printf("mxf4 N=224 2 accumulators, commit per tile=%d: %6.1f cycles/MMA\n", ce, mx / (iters * 4));
+  }
+  for (int hb : {0, 1}) {
+    const int iters = 2048;  // per warp
+    for (int rep = 0; rep < 2; ++rep) { rate2<<<148, 128, 201 * 1024>>>(224, iters, d, hb); CK(cudaDeviceSynchronize()); }
+    CK(cudaMemcpy(h, d, 148 * 8, cudaMemcpyDeviceToHost));
+    double mx = 0; for (int i = 0; i < 148; ++i) mx = h[i] > mx ? h[i] : mx;
+    printf("mxf4 N=224, two issuer warps taking turns, commit per tile, hand-off %s commit: %6.1f cycles/MMA\n", hb ? "before" : "after", mx / (2.0 * iters * 4));
+  }
+  // ---- 2b''. N sweep with a tight issue loop (the `both` kernel without readers): is there a per-MMA floor?
+  for (int N : {32, 64, 96, 112, 128, 160, 192, 224}) {
+    const long long iters = 4096;
+    for (int rep = 0; rep < 2; ++rep) { both<<<148, 384, 201 * 1024>>>(N, iters, 0, d, sink); CK(cudaDeviceSynchronize()); }
+    CK(cudaMemcpy(h, d, 148 * 8, cudaMemcpyDeviceToHost));
+    double mx = 0; for (int i = 0; i < 148; ++i) mx = h[i] > mx ? h[i] : mx;
+    printf("mxf4 N=%3d tight issue loop: %6.1f cycles/MMA (N/2 = %5.1f)\n", N, mx / (iters * 4), N / 2.0);
+  }
   // ---- 2c. MMA (warp 0) and TMEM reads (warps 4-11) at the same time
   for (int N : {224, 240}) {
     for (int readers : {0, 1}) {
@@ -437,6 +684,50 @@ int main(int argc, char** argv) {
     }
   }
 
+  // ---- 2d. mbarrier polling next to the MMAs
+  CK(cudaFuncSetAttribute(poll_vs_mma, cudaFuncAttributeMaxDynamicSharedMemorySize, 201 * 1024));
+  for (int sl : {0, 100})
+    for (int np : {0, 1, 4, 8, 12, 16}) {
+      const int iters = 4096;
+      for (int rep = 0; rep < 2; ++rep) { poll_vs_mma<<<148, 544, 201 * 1024>>>(iters, np, sl, d); CK(cudaDeviceSynchronize()); }
+      CK(cudaMemcpy(h, d, 148 * 8, cudaMemcpyDeviceToHost));
+      double mx = 0; for (int i = 0; i < 148; ++i) mx = h[i] > mx ? h[i] : mx;
+      printf("mxf4 N=224 with %2d warps polling mbarrier.try_wait (nanosleep %3d): %6.1f cycles/MMA\n", np, sl, mx / (iters * 4.0));
+    }
+  // ---- 3a. pure TMEM read bandwidth (no math): warps x loads in flight, with and without MMAs running
+  {
+    CK(cudaFuncSetAttribute(tmem_bw<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 201 * 1024));
+    CK(cudaFuncSetAttribute(tmem_bw<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 201 * 1024));
+    CK(cudaFuncSetAttribute(tmem_bw<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 201 * 1024));
+    static long long hh[148 * 16];
+    for (int with_mma : {0, 1})
+      for (int nw : {4, 8, 16})
+        for (int depth : {1, 2, 4}) {
+          const int iters = 4000;
+          for (int rep = 0; rep < 2; ++rep) {
+            if (depth == 1) tmem_bw<1><<<148, 544, 201 * 1024>>>(iters, nw, with_mma, d, sink);
+            else if (depth == 2) tmem_bw<2><<<148, 544, 201 * 1024>>>(iters, nw, with_mma, d, sink);
+            else tmem_bw<4><<<148, 544, 201 * 1024>>>(iters, nw, with_mma, d, sink);
+            CK(cudaDeviceSynchronize());
+          }
+          CK(cudaMemcpy(hh, d, sizeof hh, cudaMemcpyDeviceToHost));
+          double mx = 0; for (int w = 0; w < nw; ++w) mx = hh[w] > mx ? hh[w] : mx;
+          long long mm[2]; CK(cudaMemcpy(mm, d + 148 * 16, sizeof mm, cudaMemcpyDeviceToHost));
+          printf("tmem read: %2d warps x %d x32 loads in flight, mma=%d: %7.1f B/clk/SM", nw, depth, with_mma, (double)iters * depth * 4096.0 * nw / mx);
+          if (with_mma) printf("   MMA: %6.1f cycles each meanwhile", (double)mm[0] / (double)mm[1]);
+          printf("\n");
+        }
+  }
+  // ---- 3b. readers that also fence / fold, next to the MMAs (8 warps, 4 loads in flight)
+  for (int mode : {0, 1, 2, 3}) {
+    const int iters = 4000;
+    static long long hh2[148 * 16];
+    for (int rep = 0; rep < 2; ++rep) { tmem_bw<4><<<148, 544, 201 * 1024>>>(iters, 8, 1, d, sink, mode); CK(cudaDeviceSynchronize()); }
+    CK(cudaMemcpy(hh2, d, sizeof hh2, cudaMemcpyDeviceToHost));
+    double mx = 0; for (int w = 0; w < 8; ++w) mx = hh2[w] > mx ? hh2[w] : mx;
+    long long mm[2]; CK(cudaMemcpy(mm, d + 148 * 16, sizeof mm, cudaMemcpyDeviceToHost));
+    printf("8 reader warps, fences=%d fold=%d: %7.1f B/clk/SM read,  MMA %6.1f cycles each meanwhile\n", mode & 1, (mode >> 1) & 1, (double)iters * 4 * 4096.0 * 8 / mx, (double)mm[0] / (double)mm[1]);
+  }
   // ---- 3. TMEM read bandwidth (8 warps, 32x32b.x32 pairs)
   for (int rep = 0; rep < 2; ++rep) { tmem_read<<<148, 256>>>(2000, 256, d, sink); CK(cudaDeviceSynchronize()); }
   CK(cudaMemcpy(h, d, 148 * 8, cudaMemcpyDeviceToHost));
