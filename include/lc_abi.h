@@ -164,6 +164,22 @@ int32_t lc_match_vs_keyframe(lc_ctx* ctx, const uint8_t* q, int32_t nq, size_t q
                              int32_t* train_idx, int32_t* dist, uint8_t* good, int32_t* n_matches,
                              int32_t* min_dist, int32_t* n_good);
 
+/* One surviving match of matchFeatures: cv::DMatch(query_idx, train_idx, 0, (float)distance). */
+typedef struct lc_match {
+  int32_t query_idx;
+  int32_t train_idx;
+  int32_t distance;
+} lc_match;
+/* matchFeatures(current frame, frames_[k]) for a LIST of stored keyframes in one call, good matches compacted: what
+ * the loop candidates hand to estimatePose / triangulatePoints (include/loop_closing.hpp:43-53, README.md:101-102)
+ * without re-matching on the CPU.  matches[offsets[i] .. offsets[i + 1]) are the surviving matches against keyframe
+ * kf_index[i] in ascending query order (offsets has n_sel + 1 entries); min_dist[i] (optional) is that match's
+ * minimum distance, -1 when either side is empty.  All keyframes must be owned by this shard.  If matches_cap is too
+ * small the call fails with LC_ERR_CAPACITY after filling offsets[] with the sizes needed. */
+int32_t lc_match_keyframes(lc_ctx* ctx, const uint8_t* q, int32_t nq, size_t q_stride, int32_t n_sel,
+                           const int64_t* kf_index, lc_match* matches, int64_t matches_cap, int64_t* offsets,
+                           int32_t* min_dist);
+
 /* ---- detectLoops' data-parallel part (include/loop_closing.hpp:48): the current frame against
  *      every stored keyframe of this shard.  results[] receives one record per LOCAL keyframe in
  *      insertion order (local slot s is global keyframe shard_rank + s*shard_world); *n_results

@@ -29,6 +29,9 @@ class Config(C.Structure):
                 ("kernel", C.c_int32), ("reserved0", C.c_int32), ("slab_rows", C.c_int64)]
 
 
+MATCH = np.dtype([("query_idx", np.int32), ("train_idx", np.int32), ("distance", np.int32)])  # lc_match
+
+
 class Timing(C.Structure):
     _fields_ = [("h2d_ms", C.c_float), ("kernel_ms", C.c_float), ("d2h_ms", C.c_float), ("total_ms", C.c_float),
                 ("kernel_launches", C.c_int32), ("path", C.c_int32), ("match_ms", C.c_float), ("match_launches", C.c_int32)]
@@ -61,6 +64,7 @@ SYMBOLS = {
     "lc_db_load": (_i32, [_vp, C.c_char_p]),
     "lc_match_pair": (_i32, [_vp, _vp, _i32, _sz, _vp, _i32, _sz, _vp, _vp, _vp, _pi32, _pi32, _pi32]),
     "lc_match_vs_keyframe": (_i32, [_vp, _vp, _i32, _sz, _i64, _vp, _vp, _vp, _pi32, _pi32, _pi32]),
+    "lc_match_keyframes": (_i32, [_vp, _vp, _i32, _sz, _i32, _vp, _vp, _i64, _vp, _vp]),
     "lc_loop_check": (_i32, [_vp, _vp, _i32, _sz, _i32, _vp, _i64, _pi64, _vp]),
     "lc_loop_check_batch": (_i32, [_vp, _i32, _vp, _vp, _vp, _vp, _i64, _vp]),
     "lc_select_candidates": (_i32, [_vp, _vp, _i64, _i32, _i32, _vp, _i64, _pi64]),
@@ -248,6 +252,18 @@ class Context:
         self._ck(self._lib.lc_match_vs_keyframe(self._h, _ptr(qa), len(qa), qs, int(kf_index), _ptr(idx), _ptr(dist),
                                                 _ptr(good), C.byref(nm), C.byref(mn), C.byref(ng)))
         return self._pair_ret(idx, dist, good, nm, mn, ng)
+
+    def match_keyframes(self, q, kf_indices):
+        """matchFeatures(q, stored keyframe k) for every k in kf_indices, good matches only: a list of (MATCH array,
+        min_dist) - MATCH has fields query_idx / train_idx / distance, the cv::DMatch a pose estimator consumes."""
+        qa, qs = _rows(q, "query")
+        sel = np.ascontiguousarray(kf_indices, np.int64)
+        offs = np.zeros(len(sel) + 1, np.int64)
+        mind = np.zeros(max(len(sel), 1), np.int32)
+        buf = np.zeros(max(len(qa) * len(sel), 1), MATCH)  # an upper bound: every query survives
+        self._ck(self._lib.lc_match_keyframes(self._h, _ptr(qa), len(qa), qs, len(sel), _ptr(sel), _ptr(buf), len(buf),
+                                              _ptr(offs), _ptr(mind)))
+        return [(buf[offs[i]:offs[i + 1]].copy(), int(mind[i])) for i in range(len(sel))]
 
     # ---- detectLoops
     def loop_check(self, q, current_frame_id, want_best=True):

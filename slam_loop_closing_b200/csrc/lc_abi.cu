@@ -961,6 +961,63 @@ LC_API int32_t lc_match_pair_device(lc_ctx* c, const void* d_q, int32_t nq, cons
   LC_GUARD_END(c)
 }
 
+LC_API int32_t lc_match_keyframes(lc_ctx* c, const uint8_t* q, int32_t nq, size_t qs, int32_t n_sel, const int64_t* kf_index,
+                                  lc_match* matches, int64_t cap, int64_t* offsets, int32_t* min_dist) {
+  if (!c) return LC_ERR_INVALID;
+  LC_GUARD_BEGIN
+  LC_TRY(check_rows(c, "query", q, nq, qs));
+  if (n_sel < 0 || (n_sel > 0 && !kf_index) || !offsets || cap < 0 || (cap > 0 && !matches)) return fail(c, LC_ERR_INVALID, "bad arguments");
+  std::vector<KfEntry> sel((size_t)n_sel);
+  for (int32_t i = 0; i < n_sel; ++i) {
+    size_t s;
+    LC_TRY(find_local(c, kf_index[i], &s));
+    sel[i] = c->h_kf[s];
+  }
+  offsets[0] = 0;
+  if (n_sel == 0) return LC_OK;
+  LC_CUDA(c, cudaSetDevice(c->cfg.device));
+  timing_begin(c);
+  LC_TRY(stage_query(c, c->d_q, q, nq, qs));
+  // per keyframe on the device: idx[nq] dist[nq] summary[2] good[nq], slices 16-byte aligned
+  const size_t off_dist = (size_t)nq * 4, off_sum = off_dist + (size_t)nq * 4, off_good = off_sum + 8;
+  const size_t slice = (off_good + (size_t)nq + 15) & ~size_t(15);
+  LC_TRY(ensure(c, c->d_out, slice * (size_t)n_sel));
+  LC_TRY(ensure_pin_down(c, slice * (size_t)n_sel));
+  LC_CUDA(c, cudaEventRecord(c->ev[1], c->stream));
+  for (int32_t i = 0; i < n_sel; ++i) {
+    uint8_t* d = (uint8_t*)c->d_out.p + slice * (size_t)i;
+    if (nq == 0 || sel[i].n == 0) {  // cv::BFMatcher returns no matches when either side is empty
+      const int32_t none[2] = {-1, 0};
+      LC_CUDA(c, cudaMemcpyAsync(d + off_sum, none, sizeof none, cudaMemcpyHostToDevice, c->stream));
+      continue;
+    }
+    LC_TRY(pair_device_impl(c, c->stream, c->d_q.p, nq, sel[i], PairOut{(int32_t*)d, (int32_t*)(d + off_dist), d + off_good, (int32_t*)(d + off_sum)}));
+  }
+  LC_CUDA(c, cudaEventRecord(c->ev[2], c->stream));
+  LC_CUDA(c, cudaMemcpyAsync(c->pin_down, c->d_out.p, slice * (size_t)n_sel, cudaMemcpyDeviceToHost, c->stream));
+  LC_TRY(timing_end(c));
+  int64_t total = 0;
+  for (int32_t i = 0; i < n_sel; ++i) {
+    const uint8_t* h = c->pin_down + slice * (size_t)i;
+    int32_t sum[2];
+    memcpy(sum, h + off_sum, 8);
+    if (min_dist) min_dist[i] = sum[0];
+    const bool empty = nq == 0 || sel[i].n == 0;
+    const int32_t* idx = (const int32_t*)h;
+    const int32_t* dist = (const int32_t*)(h + off_dist);
+    const uint8_t* good = h + off_good;
+    for (int32_t j = 0; !empty && j < nq; ++j) {
+      if (!good[j]) continue;
+      if (total < cap) matches[total] = lc_match{j, idx[j], dist[j]};
+      ++total;
+    }
+    offsets[i + 1] = total;
+  }
+  if (total > cap) return fail(c, LC_ERR_CAPACITY, "matches_cap %lld < %lld", (long long)cap, (long long)total);
+  return LC_OK;
+  LC_GUARD_END(c)
+}
+
 // ------------------------------------------------------------------- detectLoops
 LC_API int32_t lc_loop_check_batch_device(lc_ctx* c, int32_t n_frames, const void* d_q, const int32_t* nq, const int32_t* cur_ids,
                                           lc_kf_result* d_results, uint64_t* d_best, void* cuda_stream) {

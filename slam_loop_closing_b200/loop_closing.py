@@ -70,6 +70,9 @@ class B200Matcher:
         res, _ = self.ctx.loop_check(q, current_frame_id, want_best=False)
         return res
 
+    def match_keyframes(self, q, kf_indices):
+        return self.ctx.match_keyframes(q, kf_indices)
+
     def close(self):
         self.ctx.close()
 
@@ -186,6 +189,21 @@ class LoopClosingSystem:
             over = sim >= self.loop_threshold_ if self.thr_inclusive_ else sim > self.loop_threshold_
             if over and int(r["n_good"]) >= self.min_good_:  # README.md:123-124
                 out.append(LoopCandidate(int(current_frame_id), int(r["frame_id"]), int(r["n_good"]), sim))
+        return out
+
+    def loopMatches(self, current_frame_id: int, loops: List[LoopCandidate]) -> dict:
+        """matchFeatures(current, matched frame) for every loop candidate in ONE GPU call (lc_match_keyframes): the
+        DMatch lists estimatePose / triangulatePoints (hpp:43-53) need to verify a loop geometrically, without
+        matching again on the CPU.  Returns {matched_frame_id: [DMatch]}."""
+        cur = next((f for f in reversed(self.frames_) if f.id == current_frame_id), None)
+        if cur is None or not loops:
+            return {}
+        index_of = {f.id: i for i, f in enumerate(self.frames_)}  # frames_ and the device store share insertion order
+        sel = [index_of[c.matched_frame_id] for c in loops]
+        out = {}
+        for c, (m, _) in zip(loops, self.matcher_.match_keyframes(cur.descriptors, sel)):
+            out[c.matched_frame_id] = [DMatch(int(a), int(b), 0, float(d)) for a, b, d in
+                                       zip(m["query_idx"], m["train_idx"], m["distance"])]
         return out
 
     # ------------------------------------------------------------------ accessors / output

@@ -287,6 +287,34 @@ def test_match_vs_keyframe_resident(lc):
         assert len(c.match_vs_keyframe(q, 2)["dist"]) == 0
 
 
+def test_match_keyframes_compacted_candidate_matches(lc):
+    """lc_match_keyframes: the DMatch lists the loop candidates hand to estimatePose (include/loop_closing.hpp:43-53)."""
+    p = Params(loop_threshold=0.15, min_loop_gap=30)
+    q = datagen.uniform(700, 5)
+    kfs = datagen.structured_db(q, 40, n=600, every=4, ragged=True)
+    kfs[9] = np.zeros((0, 32), np.uint8)
+    with _ctx(lc, p) as c:
+        c.db_append_many(list(range(40)), kfs)
+        sel = [0, 4, 9, 17, 39, 4]
+        got = c.match_keyframes(q, sel)
+        assert len(got) == len(sel)
+        for k, (m, mind) in zip(sel, got):
+            want = c_oracle.match_features(q, kfs[k], p) if len(kfs[k]) else None
+            if want is None:
+                assert len(m) == 0 and mind == -1
+                continue
+            keep = np.flatnonzero(want["good"])
+            np.testing.assert_array_equal(m["query_idx"], keep)
+            np.testing.assert_array_equal(m["train_idx"], want["train_idx"][keep])
+            np.testing.assert_array_equal(m["distance"], want["dist"][keep])
+            assert mind == want["min_dist"] and len(m) == want["n_good"]
+            if cv2_ref.available():
+                ref = cv2_ref.match_features(q, kfs[k], p)
+                np.testing.assert_array_equal(m["train_idx"], ref["train_idx"][np.flatnonzero(ref["good"])])
+        assert c.match_keyframes(q, []) == []
+        assert all(len(m) == 0 and d == -1 for m, d in c.match_keyframes(np.zeros((0, 32), np.uint8), [1, 2]))
+
+
 def test_sharded_contexts_merge_equals_single(lc):
     """two shard contexts on one GPU: merged per-keyframe records and min-merged best == unsharded."""
     p = Params(loop_threshold=0.15, min_loop_gap=10)
