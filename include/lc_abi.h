@@ -188,6 +188,14 @@ int32_t lc_match_keyframes(lc_ctx* ctx, const uint8_t* q, int32_t nq, size_t q_s
  *      (= OpenCV's multi-image tie-break); UINT64_MAX if nothing was compared. ---- */
 int32_t lc_loop_check(lc_ctx* ctx, const uint8_t* q, int32_t nq, size_t q_stride, int32_t current_frame_id,
                       lc_kf_result* results, int64_t results_cap, int64_t* n_results, uint64_t* best_packed);
+/* The same in two halves, so that the host can run ORB detection of the next frame (or anything else) while the GPU
+ * scans the store: _begin copies the query, queues upload + kernels + result download on the context's stream and
+ * returns at once; _end waits and hands out what lc_loop_check would have returned (*n_results records).  Between the
+ * two no other call on this context is allowed except lc_synchronize / lc_last_error / lc_db_size. */
+int32_t lc_loop_check_begin(lc_ctx* ctx, const uint8_t* q, int32_t nq, size_t q_stride, int32_t current_frame_id,
+                            int32_t want_best);
+int32_t lc_loop_check_end(lc_ctx* ctx, lc_kf_result* results, int64_t results_cap, int64_t* n_results,
+                          uint64_t* best_packed);
 /* Throughput mode: n_frames query frames in one call.  results is [n_frames][n_local_keyframes];
  * best_packed (optional) is the concatenation of the frames' nq[i]-entry arrays. */
 int32_t lc_loop_check_batch(lc_ctx* ctx, int32_t n_frames, const uint8_t* const* q, const int32_t* nq,

@@ -65,6 +65,8 @@ SYMBOLS = {
     "lc_match_pair": (_i32, [_vp, _vp, _i32, _sz, _vp, _i32, _sz, _vp, _vp, _vp, _pi32, _pi32, _pi32]),
     "lc_match_vs_keyframe": (_i32, [_vp, _vp, _i32, _sz, _i64, _vp, _vp, _vp, _pi32, _pi32, _pi32]),
     "lc_match_keyframes": (_i32, [_vp, _vp, _i32, _sz, _i32, _vp, _vp, _i64, _vp, _vp]),
+    "lc_loop_check_begin": (_i32, [_vp, _vp, _i32, _sz, _i32, _i32]),
+    "lc_loop_check_end": (_i32, [_vp, _vp, _i64, _vp, _vp]),
     "lc_loop_check": (_i32, [_vp, _vp, _i32, _sz, _i32, _vp, _i64, _pi64, _vp]),
     "lc_loop_check_batch": (_i32, [_vp, _i32, _vp, _vp, _vp, _vp, _i64, _vp]),
     "lc_select_candidates": (_i32, [_vp, _vp, _i64, _i32, _i32, _vp, _i64, _pi64]),
@@ -274,6 +276,21 @@ class Context:
         n = C.c_int64()
         self._ck(self._lib.lc_loop_check(self._h, _ptr(qa), len(qa), qs, int(current_frame_id), _ptr(res), nloc,
                                          C.byref(n), _ptr(best) if want_best else None))
+        return res[:n.value], best
+
+    def loop_check_begin(self, q, current_frame_id, want_best=True):
+        """Queue a loop check and return at once (the library has copied q); collect with loop_check_end()."""
+        qa, qs = _rows(q, "query")
+        self._ck(self._lib.lc_loop_check_begin(self._h, _ptr(qa), len(qa), qs, int(current_frame_id), int(bool(want_best))))
+        self._pending = (len(qa), bool(want_best))
+
+    def loop_check_end(self):
+        nq, want_best = self._pending
+        nloc = self.db_size()["local_keyframes"]
+        res = np.zeros(nloc, KF_RESULT)
+        best = np.full(nq, UINT64_MAX, np.uint64) if want_best else None
+        n = C.c_int64()
+        self._ck(self._lib.lc_loop_check_end(self._h, _ptr(res), nloc, C.byref(n), _ptr(best) if want_best else None))
         return res[:n.value], best
 
     def loop_check_batch(self, queries, current_frame_ids, want_best=True):

@@ -69,6 +69,15 @@ struct lc_ctx {
 
   lc_timing timing{};
   int64_t launches = 0;
+  // host-buffer loop check split in two (lc_loop_check_begin / _end): what the queued half left for the other
+  struct Pending {
+    bool active = false, queued = false;
+    size_t res_bytes = 0, best_bytes = 0;
+    int64_t n_res = 0, rows = 0;
+  } pending;
+  // last CTA plan of the tensor paths (run_match): valid for the same tile counts per query block and batch size
+  long long plan_kc = -1;
+  std::vector<int> plan_tiles, plan_ns;
   // event pairs around the launches of the matching kernel of the current host-buffer call (lc_timing.match_ms)
   std::vector<cudaEvent_t> match_ev;
   size_t match_ev_used = 0;
@@ -333,15 +342,52 @@ int run_match(lc_ctx* c, cudaStream_t st, const KfEntry* d_kfs, int n_kf, int ma
       }
     const int n_ab = (int)blocks.size();
     if ((long long)n_ab * n_kf >= c->num_sms) {
-      // CTAs per query block: proportional to its number of 128-row tiles (a ragged last block gets fewer); about one
-      // CTA per SM in total while the blocks fit in half the machine, else enough CTAs for >= 4 waves
-      const long long target = 2 * n_ab <= c->num_sms ? c->num_sms : 4ll * c->num_sms;
-      std::vector<tc::CtaWork> work;
-      for (int i = 0; i < n_ab; ++i) {
-        long long ns = std::max<long long>(1, (target * tiles[i]) / total_tiles);
-        ns = std::min<long long>(ns, n_kf);
-        for (int s = 0; s < (int)ns; ++s) work.push_back(tc::CtaWork{i, s, (int)ns});
+      // scratch: one distance (mxf4: u16) or key (int8: u32) per (frame, keyframe, query); rows start 16-byte aligned.
+      // The keyframes go through in batches of kc_max bounded by the scratch budget.
+      const int stride = (max_nq + 7) & ~7;
+      const size_t elem = want_fp4 ? 2 : 4;
+      long long kc_max = std::max<long long>(1, (long long)(kScratchBudgetBytes / ((size_t)stride * elem)) / n_frames);
+      kc_max = std::min<long long>(kc_max, n_kf);
+      // CTAs per query block (each takes every ns-th keyframe of a batch): proportional to the block's number of 128-row
+      // tiles, their total a whole number m of waves of one CTA per SM.  m is searched: more waves quantise better
+      // (128 query blocks on 148 SMs need 37 CTAs each = 32 waves), fewer reload the resident queries less often.
+      std::vector<int> ns_best((size_t)n_ab, 1);
+      double cost_best = 1e300;
+      const bool cached = c->plan_kc == kc_max && c->plan_tiles == tiles;  // the plan depends on nothing else
+      if (cached) ns_best = c->plan_ns;
+      for (int m = 1; m <= 32 && !cached; ++m) {
+        const long long total = (long long)m * c->num_sms;
+        if (total < n_ab && m < 32) continue;
+        std::vector<int> ns((size_t)n_ab);
+        long long used = 0;
+        for (int i = 0; i < n_ab; ++i) {
+          ns[i] = (int)std::min<long long>(kc_max, std::max<long long>(1, total * tiles[i] / total_tiles));
+          used += ns[i];
+        }
+        // hand the rounding remainder to the blocks whose CTAs carry the most work
+        for (long long left = total - used; left > 0; --left) {
+          int arg = -1;
+          double w = -1;
+          for (int i = 0; i < n_ab; ++i) {
+            const double wi = (double)tiles[i] * (double)((kc_max + ns[i] - 1) / ns[i]);
+            if (ns[i] < kc_max && wi > w) w = wi, arg = i;
+          }
+          if (arg < 0) break;
+          ns[arg] += 1;
+          used += 1;
+        }
+        double wmax = 0;
+        for (int i = 0; i < n_ab; ++i) wmax = std::max(wmax, (double)tiles[i] * (double)((kc_max + ns[i] - 1) / ns[i]));
+        // makespan in tile-keyframes: waves x the slowest CTA, plus one resident-query load (~a tenth of a keyframe) per wave
+        const double waves = (double)((used + c->num_sms - 1) / c->num_sms);
+        const double cost = waves * (wmax + 0.1 * tc::kQTilesPerCta);
+        if (cost < cost_best * 0.995) cost_best = cost, ns_best = ns;
+        if (n_ab <= 4 && m >= 2) break;  // a few blocks: one or two waves are always enough
       }
+      if (!cached) c->plan_kc = kc_max, c->plan_tiles = tiles, c->plan_ns = ns_best;
+      std::vector<tc::CtaWork> work;
+      for (int i = 0; i < n_ab; ++i)
+        for (int s = 0; s < ns_best[i]; ++s) work.push_back(tc::CtaWork{i, s, ns_best[i]});
       LC_TRY(ensure(c, c->d_qimg, (size_t)n_ab * img_bytes));
       LC_TRY(ensure(c, c->d_ablocks, (size_t)n_ab * sizeof(tc::ABlock) + work.size() * sizeof(tc::CtaWork)));
       for (int i = 0; i < n_ab; ++i) blocks[i].img = (const uint8_t*)c->d_qimg.p + (size_t)i * img_bytes;
@@ -360,11 +406,6 @@ int run_match(lc_ctx* c, cudaStream_t st, const KfEntry* d_kfs, int n_kf, int ma
         LC_CUDA(c, cudaFuncSetAttribute(fx::mxf4_match_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, fx::kSmemAlloc));
         attr_set = true;
       }
-      // scratch: one distance (mxf4: u16) or key (int8: u32) per (frame, keyframe, query); rows start 16-byte aligned
-      const int stride = (max_nq + 7) & ~7;
-      const size_t elem = want_fp4 ? 2 : 4;
-      long long kc_max = std::max<long long>(1, (long long)(kScratchBudgetBytes / ((size_t)stride * elem)) / n_frames);
-      kc_max = std::min<long long>(kc_max, n_kf);
       LC_TRY(ensure(c, c->d_scratch, (size_t)kc_max * n_frames * stride * elem));
       c->launches += 1;
       c->timing.kernel_launches += 1;
@@ -1037,19 +1078,22 @@ LC_API int32_t lc_loop_check_device(lc_ctx* c, const void* d_q, int32_t nq, int3
   return lc_loop_check_batch_device(c, 1, d_q, &nq, &cur_id, d_results, d_best, cuda_stream);
 }
 
-LC_API int32_t lc_loop_check_batch(lc_ctx* c, int32_t n_frames, const uint8_t* const* q, const int32_t* nq, const int32_t* cur_ids,
-                                   lc_kf_result* results, int64_t results_cap, uint64_t* best_packed) {
-  if (!c) return LC_ERR_INVALID;
-  LC_GUARD_BEGIN
+namespace {
+
+// first half of a host-buffer loop check: upload, kernels, D2H into the pinned result buffer - all queued, nothing waited for
+int loop_check_enqueue(lc_ctx* c, int32_t n_frames, const uint8_t* const* q, const int32_t* nq, const int32_t* cur_ids, bool want_best) {
+  if (c->pending.active) return fail(c, LC_ERR_INVALID, "a loop check is pending: call lc_loop_check_end first");
   if (n_frames < 0 || (n_frames > 0 && (!q || !nq || !cur_ids))) return fail(c, LC_ERR_INVALID, "bad arguments");
   const int64_t n_kf = (int64_t)c->h_kf.size();
-  const int64_t n_res = n_kf * n_frames;
-  if (n_res > 0 && (!results || results_cap < n_res)) return fail(c, LC_ERR_CAPACITY, "results_cap %lld < %lld", (long long)results_cap, (long long)n_res);
   int64_t rows = 0;
   for (int f = 0; f < n_frames; ++f) {
     LC_TRY(check_rows(c, "query", q[f], nq[f], LC_DESC_BYTES));
     rows += nq[f];
   }
+  c->pending = lc_ctx::Pending{};
+  c->pending.active = true;
+  c->pending.n_res = n_kf * n_frames;
+  c->pending.rows = rows;
   if (n_frames == 0) return LC_OK;
   LC_CUDA(c, cudaSetDevice(c->cfg.device));
   timing_begin(c);
@@ -1059,20 +1103,79 @@ LC_API int32_t lc_loop_check_batch(lc_ctx* c, int32_t n_frames, const uint8_t* c
     if (nq[f] > 0) LC_TRY(upload_rows(c, (uint8_t*)c->d_q.p + (size_t)r0 * LC_DESC_BYTES, q[f], nq[f], LC_DESC_BYTES));
     r0 += nq[f];
   }
-  const size_t res_bytes = (size_t)n_res * sizeof(lc_kf_result), best_bytes = best_packed ? (size_t)rows * 8 : 0;
+  const size_t res_bytes = (size_t)c->pending.n_res * sizeof(lc_kf_result), best_bytes = want_best ? (size_t)rows * 8 : 0;
   LC_TRY(ensure(c, c->d_results, std::max<size_t>(res_bytes, 16)));
   LC_TRY(ensure(c, c->d_best, std::max<size_t>(best_bytes, 16)));
   LC_TRY(ensure_pin_down(c, res_bytes + best_bytes + 16));
   LC_CUDA(c, cudaEventRecord(c->ev[1], c->stream));
   LC_TRY(loop_check_device_impl(c, c->stream, n_frames, c->d_q.p, nq, cur_ids, (lc_kf_result*)c->d_results.p,
-                                best_packed ? (uint64_t*)c->d_best.p : nullptr));
+                                want_best ? (uint64_t*)c->d_best.p : nullptr));
   LC_CUDA(c, cudaEventRecord(c->ev[2], c->stream));
   if (res_bytes) LC_CUDA(c, cudaMemcpyAsync(c->pin_down, c->d_results.p, res_bytes, cudaMemcpyDeviceToHost, c->stream));
   if (best_bytes) LC_CUDA(c, cudaMemcpyAsync(c->pin_down + res_bytes, c->d_best.p, best_bytes, cudaMemcpyDeviceToHost, c->stream));
-  LC_TRY(timing_end(c));
-  if (res_bytes) memcpy(results, c->pin_down, res_bytes);
-  if (best_bytes) memcpy(best_packed, c->pin_down + res_bytes, best_bytes);
+  LC_CUDA(c, cudaEventRecord(c->ev[3], c->stream));
+  c->pending.res_bytes = res_bytes;
+  c->pending.best_bytes = best_bytes;
+  c->pending.queued = true;
   return LC_OK;
+}
+
+// second half: wait for the queued work and hand the results out
+int loop_check_collect(lc_ctx* c, lc_kf_result* results, int64_t results_cap, uint64_t* best_packed) {
+  if (!c->pending.active) return fail(c, LC_ERR_INVALID, "no loop check is pending");
+  const lc_ctx::Pending p = c->pending;
+  c->pending.active = false;
+  if (p.queued) {
+    LC_CUDA(c, cudaSetDevice(c->cfg.device));
+    LC_TRY(timing_end(c));
+  }
+  if (p.n_res > 0 && (!results || results_cap < p.n_res))
+    return fail(c, LC_ERR_CAPACITY, "results_cap %lld < %lld", (long long)results_cap, (long long)p.n_res);
+  if (best_packed && p.rows > 0 && !p.best_bytes && p.queued) return fail(c, LC_ERR_INVALID, "the pending check was started without want_best");
+  if (p.res_bytes) memcpy(results, c->pin_down, p.res_bytes);
+  if (p.best_bytes && best_packed) memcpy(best_packed, c->pin_down + p.res_bytes, p.best_bytes);
+  return LC_OK;
+}
+
+}  // namespace
+
+LC_API int32_t lc_loop_check_batch(lc_ctx* c, int32_t n_frames, const uint8_t* const* q, const int32_t* nq, const int32_t* cur_ids,
+                                   lc_kf_result* results, int64_t results_cap, uint64_t* best_packed) {
+  if (!c) return LC_ERR_INVALID;
+  LC_GUARD_BEGIN
+  const int64_t n_res = (int64_t)c->h_kf.size() * std::max(n_frames, 0);
+  if (n_res > 0 && (!results || results_cap < n_res)) return fail(c, LC_ERR_CAPACITY, "results_cap %lld < %lld", (long long)results_cap, (long long)n_res);
+  const int rc = loop_check_enqueue(c, n_frames, q, nq, cur_ids, best_packed != nullptr);
+  if (rc != LC_OK) {
+    c->pending.active = false;
+    return rc;
+  }
+  return loop_check_collect(c, results, results_cap, best_packed);
+  LC_GUARD_END(c)
+}
+
+LC_API int32_t lc_loop_check_begin(lc_ctx* c, const uint8_t* q, int32_t nq, size_t qs, int32_t cur_id, int32_t want_best) {
+  if (!c) return LC_ERR_INVALID;
+  LC_GUARD_BEGIN
+  LC_TRY(check_rows(c, "query", q, nq, qs));
+  std::vector<uint8_t> packed;
+  const uint8_t* p = q;
+  if (qs != LC_DESC_BYTES && nq > 0) {  // strided cv::Mat: make the rows contiguous
+    packed.resize((size_t)nq * LC_DESC_BYTES);
+    for (int32_t i = 0; i < nq; ++i) memcpy(packed.data() + (size_t)i * LC_DESC_BYTES, q + (size_t)i * qs, LC_DESC_BYTES);
+    p = packed.data();
+  }
+  const int rc = loop_check_enqueue(c, 1, &p, &nq, &cur_id, want_best != 0);  // upload_rows has copied the rows when this returns
+  if (rc != LC_OK) c->pending.active = false;
+  return rc;
+  LC_GUARD_END(c)
+}
+
+LC_API int32_t lc_loop_check_end(lc_ctx* c, lc_kf_result* results, int64_t results_cap, int64_t* n_results, uint64_t* best_packed) {
+  if (!c) return LC_ERR_INVALID;
+  LC_GUARD_BEGIN
+  if (n_results) *n_results = c->pending.active ? c->pending.n_res : 0;
+  return loop_check_collect(c, results, results_cap, best_packed);
   LC_GUARD_END(c)
 }
 

@@ -315,6 +315,30 @@ def test_match_keyframes_compacted_candidate_matches(lc):
         assert all(len(m) == 0 and d == -1 for m, d in c.match_keyframes(np.zeros((0, 32), np.uint8), [1, 2]))
 
 
+def test_loop_check_begin_end_overlaps_host_work(lc):
+    """lc_loop_check_begin / _end: the same results as lc_loop_check, with the host free in between."""
+    p = Params(loop_threshold=0.15, min_loop_gap=30)
+    q = datagen.uniform(2000, 21)
+    kfs = datagen.structured_db(q, 600, n=500, every=9, ragged=True)
+    with _ctx(lc, p) as c:
+        c.db_append_many(list(range(600)), kfs)
+        want_res, want_best = c.loop_check(q, 700)
+        c.loop_check_begin(q, 700)
+        q[:] = 0  # the library copied the rows: the caller's buffer is free again
+        busy = sum(int(x) for x in np.arange(20000))  # "ORB of the next frame"
+        with pytest.raises(lc.LcError):  # no second check while one is pending
+            c.loop_check(datagen.uniform(10, 1), 700)
+        res, best = c.loop_check_end()
+        assert busy > 0
+        np.testing.assert_array_equal(res, want_res)
+        np.testing.assert_array_equal(best, want_best)
+        with pytest.raises(lc.LcError):
+            c.loop_check_end()  # nothing pending any more
+        c.loop_check_begin(datagen.uniform(300, 2), 700, want_best=False)
+        res2, best2 = c.loop_check_end()
+        assert best2 is None and len(res2) == 600
+
+
 def test_sharded_contexts_merge_equals_single(lc):
     """two shard contexts on one GPU: merged per-keyframe records and min-merged best == unsharded."""
     p = Params(loop_threshold=0.15, min_loop_gap=10)
