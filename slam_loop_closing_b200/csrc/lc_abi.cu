@@ -75,6 +75,10 @@ struct lc_ctx {
     size_t res_bytes = 0, best_bytes = 0;
     int64_t n_res = 0, rows = 0;
   } pending;
+  bool smem_attr_set = false;  // the tensor kernels' dynamic shared-memory limit has been raised on this device
+  // what d_ablocks holds (query-block + CTA tables of the tensor paths), to skip identical uploads
+  const void* tables_dev = nullptr;
+  std::vector<uint8_t> tables_host;
   // last CTA plan of the tensor paths (run_match): valid for the same tile counts per query block and batch size
   long long plan_kc = -1;
   std::vector<int> plan_tiles, plan_ns;
@@ -389,22 +393,31 @@ int run_match(lc_ctx* c, cudaStream_t st, const KfEntry* d_kfs, int n_kf, int ma
       for (int i = 0; i < n_ab; ++i)
         for (int s = 0; s < ns_best[i]; ++s) work.push_back(tc::CtaWork{i, s, ns_best[i]});
       LC_TRY(ensure(c, c->d_qimg, (size_t)n_ab * img_bytes));
+      const size_t tables_cap = c->d_ablocks.cap;
       LC_TRY(ensure(c, c->d_ablocks, (size_t)n_ab * sizeof(tc::ABlock) + work.size() * sizeof(tc::CtaWork)));
+      if (c->d_ablocks.cap != tables_cap) c->tables_dev = nullptr;  // a new allocation holds nothing yet
       for (int i = 0; i < n_ab; ++i) blocks[i].img = (const uint8_t*)c->d_qimg.p + (size_t)i * img_bytes;
       tc::ABlock* d_blocks = (tc::ABlock*)c->d_ablocks.p;
       tc::CtaWork* d_work = (tc::CtaWork*)(d_blocks + n_ab);
-      LC_CUDA(c, cudaMemcpyAsync(d_blocks, blocks.data(), (size_t)n_ab * sizeof(tc::ABlock), cudaMemcpyHostToDevice, st));
-      LC_CUDA(c, cudaMemcpyAsync(d_work, work.data(), work.size() * sizeof(tc::CtaWork), cudaMemcpyHostToDevice, st));
+      {  // one upload for both tables, skipped when the device copy is already this (same shapes, same buffers)
+        std::vector<uint8_t> img((size_t)n_ab * sizeof(tc::ABlock) + work.size() * sizeof(tc::CtaWork));
+        memcpy(img.data(), blocks.data(), (size_t)n_ab * sizeof(tc::ABlock));
+        memcpy(img.data() + (size_t)n_ab * sizeof(tc::ABlock), work.data(), work.size() * sizeof(tc::CtaWork));
+        if (c->tables_dev != (const void*)d_blocks || c->tables_host != img) {
+          LC_CUDA(c, cudaMemcpyAsync(d_blocks, img.data(), img.size(), cudaMemcpyHostToDevice, st));
+          c->tables_dev = d_blocks;
+          c->tables_host.swap(img);
+        }
+      }
       if (want_fp4)
         fx::expand_queries_fp4_kernel<<<n_ab, 512, 0, st>>>((const fx::ABlock*)d_blocks, d_frames, (uint8_t*)c->d_qimg.p);
       else
         tc::expand_queries_kernel<<<n_ab, 256, 0, st>>>(d_blocks, d_frames, (uint8_t*)c->d_qimg.p);
       LC_CUDA(c, cudaGetLastError());
-      static bool attr_set = false;
-      if (!attr_set) {
+      if (!c->smem_attr_set) {  // per device, so per context
         LC_CUDA(c, cudaFuncSetAttribute(tc::tensor_match_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kSmemAlloc));
         LC_CUDA(c, cudaFuncSetAttribute(fx::mxf4_match_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, fx::kSmemAlloc));
-        attr_set = true;
+        c->smem_attr_set = true;
       }
       LC_TRY(ensure(c, c->d_scratch, (size_t)kc_max * n_frames * stride * elem));
       c->launches += 1;
@@ -1081,8 +1094,7 @@ LC_API int32_t lc_loop_check_device(lc_ctx* c, const void* d_q, int32_t nq, int3
 namespace {
 
 // first half of a host-buffer loop check: upload, kernels, D2H into the pinned result buffer - all queued, nothing waited for
-int loop_check_enqueue(lc_ctx* c, int32_t n_frames, const uint8_t* const* q, const int32_t* nq, const int32_t* cur_ids, bool want_best) {
-  if (c->pending.active) return fail(c, LC_ERR_INVALID, "a loop check is pending: call lc_loop_check_end first");
+int loop_check_enqueue_impl(lc_ctx* c, int32_t n_frames, const uint8_t* const* q, const int32_t* nq, const int32_t* cur_ids, bool want_best) {
   if (n_frames < 0 || (n_frames > 0 && (!q || !nq || !cur_ids))) return fail(c, LC_ERR_INVALID, "bad arguments");
   const int64_t n_kf = (int64_t)c->h_kf.size();
   int64_t rows = 0;
@@ -1120,6 +1132,13 @@ int loop_check_enqueue(lc_ctx* c, int32_t n_frames, const uint8_t* const* q, con
   return LC_OK;
 }
 
+int loop_check_enqueue(lc_ctx* c, int32_t n_frames, const uint8_t* const* q, const int32_t* nq, const int32_t* cur_ids, bool want_best) {
+  if (c->pending.active) return fail(c, LC_ERR_INVALID, "a loop check is pending: call lc_loop_check_end first");
+  const int rc = loop_check_enqueue_impl(c, n_frames, q, nq, cur_ids, want_best);
+  if (rc != LC_OK) c->pending.active = false;  // nothing of a failed check stays pending
+  return rc;
+}
+
 // second half: wait for the queued work and hand the results out
 int loop_check_collect(lc_ctx* c, lc_kf_result* results, int64_t results_cap, uint64_t* best_packed) {
   if (!c->pending.active) return fail(c, LC_ERR_INVALID, "no loop check is pending");
@@ -1145,11 +1164,7 @@ LC_API int32_t lc_loop_check_batch(lc_ctx* c, int32_t n_frames, const uint8_t* c
   LC_GUARD_BEGIN
   const int64_t n_res = (int64_t)c->h_kf.size() * std::max(n_frames, 0);
   if (n_res > 0 && (!results || results_cap < n_res)) return fail(c, LC_ERR_CAPACITY, "results_cap %lld < %lld", (long long)results_cap, (long long)n_res);
-  const int rc = loop_check_enqueue(c, n_frames, q, nq, cur_ids, best_packed != nullptr);
-  if (rc != LC_OK) {
-    c->pending.active = false;
-    return rc;
-  }
+  LC_TRY(loop_check_enqueue(c, n_frames, q, nq, cur_ids, best_packed != nullptr));
   return loop_check_collect(c, results, results_cap, best_packed);
   LC_GUARD_END(c)
 }
@@ -1165,9 +1180,7 @@ LC_API int32_t lc_loop_check_begin(lc_ctx* c, const uint8_t* q, int32_t nq, size
     for (int32_t i = 0; i < nq; ++i) memcpy(packed.data() + (size_t)i * LC_DESC_BYTES, q + (size_t)i * qs, LC_DESC_BYTES);
     p = packed.data();
   }
-  const int rc = loop_check_enqueue(c, 1, &p, &nq, &cur_id, want_best != 0);  // upload_rows has copied the rows when this returns
-  if (rc != LC_OK) c->pending.active = false;
-  return rc;
+  return loop_check_enqueue(c, 1, &p, &nq, &cur_id, want_best != 0);  // upload_rows has copied the rows when this returns
   LC_GUARD_END(c)
 }
 
