@@ -116,13 +116,26 @@ class ShardedLoopDB:
         cur = np.asarray(current_frame_ids, np.int32)
         rec, best = self.merged_device(d_q, nq, cur)
         K = self.n_keyframes
-        rec_np = rec.cpu().numpy().reshape(len(nq), -1, 4)[:, :K]
-        out = np.zeros((len(nq), K), _native.KF_RESULT)
-        for i, name in enumerate(("frame_id", "n_kf", "min_dist", "n_good")):
-            out[name] = rec_np[:, :, i]
-        b = best.cpu().numpy().view(np.uint64)
+        rec_h, best_h = self._to_host(rec.reshape(-1), best)  # both downloads queued, one synchronisation
+        # a merged record is four int32 in lc_kf_result order: reinterpret instead of copying field by field
+        out = rec_h.view(np.int32).reshape(len(nq), -1, 4)[:, :K].copy().view(_native.KF_RESULT).reshape(len(nq), K)
+        b = best_h.view(np.uint64)
         offs = np.concatenate([[0], np.cumsum(nq)])
-        return out, [b[offs[i]:offs[i + 1]] for i in range(len(nq))]
+        return out, [b[offs[i]:offs[i + 1]].copy() for i in range(len(nq))]
+
+    def _to_host(self, rec_flat, best):
+        """Device results -> numpy through pinned staging (CUDA tensors) or directly (the CPU test double)."""
+        if not rec_flat.is_cuda:
+            return rec_flat.numpy(), best.numpy()
+        need = (rec_flat.numel(), best.numel())
+        if getattr(self, "_pin_out", None) is None or self._pin_out[0].numel() < need[0] or self._pin_out[1].numel() < need[1]:
+            self._pin_out = (torch.empty(max(need[0], 1), dtype=torch.int32).pin_memory(),
+                             torch.empty(max(need[1], 1), dtype=torch.int64).pin_memory())
+        r, b = self._pin_out[0][:need[0]], self._pin_out[1][:need[1]]
+        r.copy_(rec_flat, non_blocking=True)
+        b.copy_(best, non_blocking=True)
+        torch.cuda.current_stream(rec_flat.device).synchronize()
+        return r.numpy(), b.numpy()
 
     def merged_device(self, d_q, nq, cur):
         """Device-resident result of the sharded check: (records int32 [F, slots*world, 4] in global keyframe
