@@ -448,6 +448,22 @@ def extras(lc, torch, q, kernel):
             ks.append(c.last_timing().kernel_ms)
         out["c3_1k_keyframes"] = {"e2e_ms_median": float(np.median(ts) * 1e3), "kernel_ms_median": float(np.median(ks)),
                                   "kernel_gpairs_s": 4e9 / (float(np.median(ks)) * 1e-3) / 1e9, "path": c.last_timing().path}
+        # the shipped pipeline's matcher (src/main.cpp:509-534): 4000 SIFT descriptors vs 300 views x 4000, knn k=2 + ratio
+        rng = np.random.default_rng(DB_SEED)
+        base = rng.integers(0, 200, (4000, 128)).astype(np.uint8)
+        for k in range(300):
+            c.l2_db_append(k, np.roll(base, k, axis=0))
+        sq = rng.integers(0, 200, (4000, 128)).astype(np.uint8)
+        for _ in range(2):
+            c.l2_loop_check(sq, 400, 1)
+        ts, ks = [], []
+        for _ in range(5):
+            t0 = time.perf_counter()
+            c.l2_loop_check(sq, 400, 1)
+            ts.append(time.perf_counter() - t0)
+            ks.append(c.last_timing().match_ms)
+        out["sift_l2_knn2_300_views_4000x4000"] = {"e2e_ms_median": float(np.median(ts) * 1e3), "kernel_ms_median": float(np.median(ks)),
+                                                  "kernel_gpairs_s_128d": 300 * 16e6 / (float(np.median(ks)) * 1e-3) / 1e9}
     return out
 
 

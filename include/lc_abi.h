@@ -224,6 +224,35 @@ int32_t lc_match_pair_device(lc_ctx* ctx, const void* d_q, int32_t nq, const voi
                              int32_t* d_train_idx, int32_t* d_dist, uint8_t* d_good, int32_t* d_summary,
                              void* cuda_stream);
 
+/* ---- the SHIPPED pipeline's matcher (src/main.cpp:509-534): SIFT descriptors, cv::BFMatcher(NORM_L2).knnMatch(k = 2)
+ *      and Lowe's ratio test  best.distance < ratio * second.distance;  its loop search (src/main.cpp:1375-1392) matches
+ *      the current view against every view at least loop_gap back, skipping pairs where a side has < min_rows rows.
+ *      Descriptors are OpenCV SIFT rows of 128 values: desc_type LC_DESC_F32 (CV_32F, the default of cv::SIFT; the
+ *      values must be integers in [0, 255], which is what cv::SIFT produces) or LC_DESC_U8 (CV_8U).  Squared distances
+ *      are exact integers, distances are sqrtf of them: bit-identical to OpenCV's.  The views live in their own
+ *      device-resident store (sharded like the ORB store). ---- */
+#define LC_L2_DIMS 128
+typedef enum lc_desc_type { LC_DESC_F32 = 0, LC_DESC_U8 = 1 } lc_desc_type;
+typedef struct lc_l2_result { /* one per stored view */
+  int32_t frame_id;
+  int32_t n_kf;
+  int32_t n_good; /* matches surviving the ratio test (matches.size() of main.cpp:1389); -1 when the pair was skipped */
+  int32_t reserved;
+} lc_l2_result;
+int32_t lc_l2_db_append(lc_ctx* ctx, int32_t frame_id, const void* desc, int32_t n, size_t row_stride, int32_t desc_type,
+                        int64_t* kf_index);
+int32_t lc_l2_db_size(const lc_ctx* ctx, int64_t* n_keyframes, int64_t* n_local_keyframes);
+int32_t lc_l2_db_clear(lc_ctx* ctx);
+/* matchFeatures(desc1 = q, desc2 = t, ratio): per query the best train row, its distance, the second distance (-1 when
+ * the train side has fewer than two rows) and whether it survives the ratio test; *n_good = goodMatches.size(). */
+int32_t lc_l2_match_pair(lc_ctx* ctx, const void* q, int32_t nq, size_t q_stride, const void* t, int32_t nt,
+                         size_t t_stride, int32_t desc_type, double ratio, int32_t* train_idx, float* distance,
+                         float* second_distance, uint8_t* good, int32_t* n_good);
+/* The loop search's matching step: results[] receives one record per LOCAL view in insertion order. */
+int32_t lc_l2_loop_check(lc_ctx* ctx, const void* q, int32_t nq, size_t q_stride, int32_t desc_type,
+                         int32_t current_frame_id, int32_t loop_gap, double ratio, int32_t min_rows,
+                         lc_l2_result* results, int64_t results_cap, int64_t* n_results);
+
 /* ---- introspection ---- */
 int32_t lc_get_last_timing(const lc_ctx* ctx, lc_timing* out);
 /* Number of kernels this context has launched since creation (bench.py's gpu_launches). */

@@ -6,7 +6,7 @@ import subprocess
 CSRC = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc")
 LIB = os.path.join(CSRC, "liblc_b200.so")
 SOURCES = ["lc_abi.cu"]
-HEADERS = ["lc_kernels.cuh", "lc_tensor.cuh", "lc_mxf4.cuh", os.path.join("..", "..", "include", "lc_abi.h")]
+HEADERS = ["lc_kernels.cuh", "lc_tensor.cuh", "lc_mxf4.cuh", "lc_l2.cuh", os.path.join("..", "..", "include", "lc_abi.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",

@@ -29,6 +29,7 @@ class Config(C.Structure):
                 ("kernel", C.c_int32), ("reserved0", C.c_int32), ("slab_rows", C.c_int64)]
 
 
+L2_RESULT = np.dtype([("frame_id", "<i4"), ("n_kf", "<i4"), ("n_good", "<i4"), ("reserved", "<i4")])  # lc_l2_result
 MATCH = np.dtype([("query_idx", np.int32), ("train_idx", np.int32), ("distance", np.int32)])  # lc_match
 
 
@@ -65,6 +66,11 @@ SYMBOLS = {
     "lc_match_pair": (_i32, [_vp, _vp, _i32, _sz, _vp, _i32, _sz, _vp, _vp, _vp, _pi32, _pi32, _pi32]),
     "lc_match_vs_keyframe": (_i32, [_vp, _vp, _i32, _sz, _i64, _vp, _vp, _vp, _pi32, _pi32, _pi32]),
     "lc_match_keyframes": (_i32, [_vp, _vp, _i32, _sz, _i32, _vp, _vp, _i64, _vp, _vp]),
+    "lc_l2_db_append": (_i32, [_vp, _i32, _vp, _i32, _sz, _i32, _vp]),
+    "lc_l2_db_size": (_i32, [_vp, _vp, _vp]),
+    "lc_l2_db_clear": (_i32, [_vp]),
+    "lc_l2_match_pair": (_i32, [_vp, _vp, _i32, _sz, _vp, _i32, _sz, _i32, C.c_double, _vp, _vp, _vp, _vp, _pi32]),
+    "lc_l2_loop_check": (_i32, [_vp, _vp, _i32, _sz, _i32, _i32, _i32, C.c_double, _i32, _vp, _i64, _vp]),
     "lc_loop_check_begin": (_i32, [_vp, _vp, _i32, _sz, _i32, _i32]),
     "lc_loop_check_end": (_i32, [_vp, _vp, _i64, _vp, _vp]),
     "lc_loop_check": (_i32, [_vp, _vp, _i32, _sz, _i32, _vp, _i64, _pi64, _vp]),
@@ -266,6 +272,54 @@ class Context:
         self._ck(self._lib.lc_match_keyframes(self._h, _ptr(qa), len(qa), qs, len(sel), _ptr(sel), _ptr(buf), len(buf),
                                               _ptr(offs), _ptr(mind)))
         return [(buf[offs[i]:offs[i + 1]].copy(), int(mind[i])) for i in range(len(sel))]
+
+    # ---- the shipped pipeline's SIFT / L2 matcher (src/main.cpp:509-534, 1375-1392)
+    @staticmethod
+    def _l2_rows(a, what):
+        a = np.asarray(a)
+        if a.dtype != np.uint8:
+            a = a.astype(np.float32, copy=False)
+        if a.ndim != 2 or a.shape[1] != 128:
+            raise ValueError(f"{what}: expected (n, 128) SIFT descriptors, got {a.shape}")
+        if a.strides[1] != a.itemsize:
+            a = np.ascontiguousarray(a)
+        return a, int(a.strides[0]) if len(a) else 128 * a.itemsize, 1 if a.dtype == np.uint8 else 0
+
+    def l2_db_append(self, frame_id, desc):
+        a, st, ty = self._l2_rows(desc, "descriptors")
+        k = C.c_int64()
+        self._ck(self._lib.lc_l2_db_append(self._h, int(frame_id), _ptr(a), len(a), st, ty, C.byref(k)))
+        return k.value
+
+    def l2_db_size(self):
+        n, nl = C.c_int64(), C.c_int64()
+        self._ck(self._lib.lc_l2_db_size(self._h, C.byref(n), C.byref(nl)))
+        return dict(keyframes=n.value, local_keyframes=nl.value)
+
+    def l2_db_clear(self):
+        self._ck(self._lib.lc_l2_db_clear(self._h))
+
+    def l2_match_pair(self, q, t, ratio=0.75):
+        """matchFeatures(desc1 = q, desc2 = t, ratio) of src/main.cpp:509: knnMatch(k = 2) + Lowe's ratio test."""
+        qa, qs, ty = self._l2_rows(q, "query")
+        ta, ts, ty2 = self._l2_rows(t, "train")
+        if ty != ty2:
+            raise ValueError("query and train descriptors must have the same dtype")
+        n = len(qa)
+        idx, dist, sec, good = np.zeros(n, np.int32), np.zeros(n, np.float32), np.zeros(n, np.float32), np.zeros(n, np.uint8)
+        ng = C.c_int32()
+        self._ck(self._lib.lc_l2_match_pair(self._h, _ptr(qa), n, qs, _ptr(ta), len(ta), ts, ty, float(ratio), _ptr(idx),
+                                            _ptr(dist), _ptr(sec), _ptr(good), C.byref(ng)))
+        return dict(train_idx=idx, distance=dist, second=sec, good=good.astype(bool), n_good=ng.value)
+
+    def l2_loop_check(self, q, current_frame_id, loop_gap, ratio=0.7, min_rows=100):
+        qa, qs, ty = self._l2_rows(q, "query")
+        nloc = self.l2_db_size()["local_keyframes"]
+        res = np.zeros(nloc, L2_RESULT)
+        n = C.c_int64()
+        self._ck(self._lib.lc_l2_loop_check(self._h, _ptr(qa), len(qa), qs, ty, int(current_frame_id), int(loop_gap),
+                                            float(ratio), int(min_rows), _ptr(res), nloc, C.byref(n)))
+        return res[:n.value]
 
     # ---- detectLoops
     def loop_check(self, q, current_frame_id, want_best=True):

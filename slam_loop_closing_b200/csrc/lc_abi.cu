@@ -8,6 +8,8 @@
 
 #include <algorithm>
 #include <cstdarg>
+#include <cmath>
+#include <cstddef>
 #include <cstdio>
 #include <cstring>
 #include <limits>
@@ -18,6 +20,7 @@
 #include "lc_kernels.cuh"
 #include "lc_tensor.cuh"
 #include "lc_mxf4.cuh"
+#include "lc_l2.cuh"
 
 using namespace lc;
 
@@ -76,6 +79,17 @@ struct lc_ctx {
     int64_t n_res = 0, rows = 0;
   } pending;
   bool smem_attr_set = false;  // the tensor kernels' dynamic shared-memory limit has been raised on this device
+  // ---- the SIFT / L2 store of the shipped pipeline's matcher (lc_l2.cuh): 128-byte rows + their squared norms
+  struct L2Store {
+    std::vector<void*> slabs;
+    size_t slab_cap = 0, slab_used = 0;
+    std::vector<l2::L2Kf> h_kf;  // local views
+    DevBuf d_kf;
+    size_t synced = 0;
+    int64_t g_kf = 0;
+  } l2s;
+  DevBuf d_l2q, d_l2t, d_l2norm, d_l2res, d_l2frames, d_l2out, d_l2img, d_l2tables;
+  bool l2_attr_set = false;
   // what d_ablocks holds (query-block + CTA tables of the tensor paths), to skip identical uploads
   const void* tables_dev = nullptr;
   std::vector<uint8_t> tables_host;
@@ -696,6 +710,9 @@ LC_API void lc_destroy(lc_ctx* c) {
   cudaSetDevice(c->cfg.device);
   if (c->stream) cudaStreamSynchronize(c->stream);
   for (void* p : c->slabs) cudaFree(p);
+  for (void* p : c->l2s.slabs) cudaFree(p);
+  for (DevBuf* b : {&c->l2s.d_kf, &c->d_l2q, &c->d_l2t, &c->d_l2norm, &c->d_l2res, &c->d_l2frames, &c->d_l2out, &c->d_l2img, &c->d_l2tables})
+    if (b->p) cudaFree(b->p);
   for (DevBuf* b : {&c->d_kf, &c->d_q, &c->d_t, &c->d_results, &c->d_best, &c->d_scratch, &c->d_frames, &c->d_pair, &c->d_out, &c->d_counter, &c->d_qimg, &c->d_ablocks})
     if (b->p) cudaFree(b->p);
   if (c->pin_up) cudaFreeHost(c->pin_up);
@@ -1237,6 +1254,251 @@ LC_API int32_t lc_detect_loops(lc_ctx* c, const uint8_t* q, int32_t nq, size_t q
   const int rc = lc_select_candidates(c, res.data(), n, nq, cur_id, out, out_cap, n_out);
   if (rc == LC_ERR_CAPACITY) return fail(c, rc, "out_cap %lld too small", (long long)out_cap);
   return rc;
+  LC_GUARD_END(c)
+}
+
+// ------------------------------------------------------------------- SIFT / L2 (the shipped pipeline's matcher)
+namespace {
+
+constexpr size_t kL2SlabBytes = 256u << 20;
+
+// OpenCV SIFT rows (CV_32F integer-valued, or CV_8U) -> contiguous u8 rows in `dst`
+int l2_to_u8(lc_ctx* c, const void* desc, int32_t n, size_t stride, int32_t type, std::vector<uint8_t>& dst) {
+  if (n < 0 || n > LC_MAX_ROWS_PER_KF) return fail(c, LC_ERR_INVALID, "n = %d outside [0, %d]", n, LC_MAX_ROWS_PER_KF);
+  if (type != LC_DESC_F32 && type != LC_DESC_U8) return fail(c, LC_ERR_INVALID, "unknown desc_type %d", type);
+  if (n > 0 && !desc) return fail(c, LC_ERR_INVALID, "NULL descriptors with n = %d", n);
+  const size_t row = type == LC_DESC_F32 ? LC_L2_DIMS * sizeof(float) : LC_L2_DIMS;
+  if (n > 0 && stride < row) return fail(c, LC_ERR_INVALID, "row_stride %zu < %zu", stride, row);
+  dst.resize((size_t)n * LC_L2_DIMS);
+  for (int32_t i = 0; i < n; ++i) {
+    const uint8_t* src = (const uint8_t*)desc + (size_t)i * stride;
+    uint8_t* out = dst.data() + (size_t)i * LC_L2_DIMS;
+    if (type == LC_DESC_U8) {
+      memcpy(out, src, LC_L2_DIMS);
+    } else {
+      const float* f = (const float*)src;
+      for (int k = 0; k < LC_L2_DIMS; ++k) {
+        const float v = f[k];
+        if (!(v >= 0.f && v <= 255.f) || v != (float)(int)v)
+          return fail(c, LC_ERR_INVALID, "row %d, element %d = %g: SIFT descriptors must be integers in [0, 255] (cv::SIFT's output)", i, k, (double)v);
+        out[k] = (uint8_t)(int)v;
+      }
+    }
+  }
+  return LC_OK;
+}
+
+// u8 rows -> device buffer (16-byte aligned rows) + their norms
+int l2_stage(lc_ctx* c, DevBuf& rows, size_t norm_off, const std::vector<uint8_t>& u8, int32_t n) {
+  LC_TRY(ensure(c, rows, (size_t)std::max(n, 1) * LC_L2_DIMS));
+  LC_TRY(ensure(c, c->d_l2norm, norm_off + (size_t)std::max(n, 1) * 4));
+  if (n > 0) {
+    LC_TRY(upload_rows(c, (uint8_t*)rows.p, u8.data(), (int64_t)n * 4, LC_DESC_BYTES));  // 128 B = four 32-byte units
+    l2::norms_kernel<<<(n + 7) / 8, 256, 0, c->stream>>>((const uint4*)rows.p, n, (uint32_t*)((uint8_t*)c->d_l2norm.p + norm_off));
+    LC_CUDA(c, cudaGetLastError());
+    c->launches += 1;
+  }
+  return LC_OK;
+}
+
+// match n_frames query frames (device tables) against n_kf views
+int l2_run(lc_ctx* c, const l2::L2Kf* d_kfs, int n_kf, const l2::L2Frame* d_frames, const l2::L2Frame* h_frames, int n_frames,
+           l2::L2Result* d_results, l2::L2Knobs kb) {
+  cudaStream_t st = c->stream;
+  const int n_items = n_kf * n_frames;
+  if (n_items == 0) return LC_OK;
+  l2::init_results_kernel<<<(n_items + 255) / 256, 256, 0, st>>>(d_kfs, n_kf, d_frames, n_frames, d_results, kb);
+  LC_CUDA(c, cudaGetLastError());
+  c->launches += 1;
+  std::vector<l2::ABlock> blocks;
+  std::vector<int> tiles;
+  long long total_tiles = 0;
+  for (int f = 0; f < n_frames; ++f)
+    for (int q0 = 0; q0 < h_frames[f].nq; q0 += l2::kQPerCta) {
+      blocks.push_back(l2::ABlock{nullptr, f, q0});
+      tiles.push_back((std::min(l2::kQPerCta, h_frames[f].nq - q0) + l2::kQTile - 1) / l2::kQTile);
+      total_tiles += tiles.back();
+    }
+  const int n_ab = (int)blocks.size();
+  if (n_ab == 0) return LC_OK;
+  std::vector<tc::CtaWork> work;
+  for (int i = 0; i < n_ab; ++i) {  // CTAs per query block: proportional to its tiles, about one CTA per SM in total
+    const int ns = (int)std::min<long long>(n_kf, std::max<long long>(1, (long long)c->num_sms * tiles[i] / total_tiles));
+    for (int s = 0; s < ns; ++s) work.push_back(tc::CtaWork{i, s, ns});
+  }
+  LC_TRY(ensure(c, c->d_l2img, (size_t)n_ab * l2::kABytes));
+  LC_TRY(ensure(c, c->d_l2tables, (size_t)n_ab * sizeof(l2::ABlock) + work.size() * sizeof(tc::CtaWork)));
+  for (int i = 0; i < n_ab; ++i) blocks[i].img = (const uint8_t*)c->d_l2img.p + (size_t)i * l2::kABytes;
+  l2::ABlock* d_blocks = (l2::ABlock*)c->d_l2tables.p;
+  tc::CtaWork* d_work = (tc::CtaWork*)(d_blocks + n_ab);
+  LC_CUDA(c, cudaMemcpyAsync(d_blocks, blocks.data(), (size_t)n_ab * sizeof(l2::ABlock), cudaMemcpyHostToDevice, st));
+  LC_CUDA(c, cudaMemcpyAsync(d_work, work.data(), work.size() * sizeof(tc::CtaWork), cudaMemcpyHostToDevice, st));
+  l2::pack_queries_kernel<<<n_ab, 512, 0, st>>>(d_blocks, d_frames, (uint8_t*)c->d_l2img.p);
+  LC_CUDA(c, cudaGetLastError());
+  if (!c->l2_attr_set) {
+    LC_CUDA(c, cudaFuncSetAttribute(l2::l2_match_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, l2::kSmemAlloc));
+    c->l2_attr_set = true;
+  }
+  {
+    MatchTimer mt(c, st);
+    l2::l2_match_kernel<<<(unsigned)work.size(), l2::kThreads, l2::kSmemAlloc, st>>>(d_kfs, n_kf, d_frames, d_blocks, d_work, d_results, kb);
+  }
+  LC_CUDA(c, cudaGetLastError());
+  c->launches += 2;
+  c->timing.kernel_launches += 3;
+  c->timing.path = 5;
+  return LC_OK;
+}
+
+}  // namespace
+
+LC_API int32_t lc_l2_db_append(lc_ctx* c, int32_t frame_id, const void* desc, int32_t n, size_t stride, int32_t type, int64_t* kf_index) {
+  if (!c) return LC_ERR_INVALID;
+  LC_GUARD_BEGIN
+  LC_CUDA(c, cudaSetDevice(c->cfg.device));
+  auto& S = c->l2s;
+  const int64_t k = S.g_kf;
+  const bool own = (k % c->cfg.shard_world) == c->cfg.shard_rank;
+  if (n < 0 || n > LC_MAX_ROWS_PER_KF) return fail(c, LC_ERR_INVALID, "n = %d outside [0, %d]", n, LC_MAX_ROWS_PER_KF);
+  if (own) {
+    std::vector<uint8_t> u8;
+    LC_TRY(l2_to_u8(c, desc, n, stride, type, u8));
+    // rows (128 B each) followed by the norms (4 B each), 256-byte aligned, inside one slab
+    const size_t need = (((size_t)n * LC_L2_DIMS + 255) & ~size_t(255)) + (((size_t)n * 4 + 255) & ~size_t(255));
+    if (S.slabs.empty() || S.slab_used + need > S.slab_cap) {
+      const size_t cap = std::max(kL2SlabBytes, need);
+      void* p = nullptr;
+      LC_CUDA(c, cudaMalloc(&p, std::max<size_t>(cap, 256)));
+      S.slabs.push_back(p);
+      S.slab_cap = cap;
+      S.slab_used = 0;
+    }
+    uint8_t* rows = (uint8_t*)S.slabs.back() + S.slab_used;
+    uint32_t* norms = (uint32_t*)(rows + (((size_t)n * LC_L2_DIMS + 255) & ~size_t(255)));
+    S.slab_used += need;
+    if (n > 0) {
+      LC_TRY(upload_rows(c, rows, u8.data(), (int64_t)n * 4, LC_DESC_BYTES));
+      l2::norms_kernel<<<(n + 7) / 8, 256, 0, c->stream>>>((const uint4*)rows, n, norms);
+      LC_CUDA(c, cudaGetLastError());
+      c->launches += 1;
+    }
+    S.h_kf.push_back(l2::L2Kf{(const uint4*)rows, norms, n, frame_id});
+  }
+  if (kf_index) *kf_index = k;
+  S.g_kf += 1;
+  return LC_OK;
+  LC_GUARD_END(c)
+}
+
+LC_API int32_t lc_l2_db_size(const lc_ctx* c, int64_t* n_kf, int64_t* n_local) {
+  if (!c) return LC_ERR_INVALID;
+  if (n_kf) *n_kf = c->l2s.g_kf;
+  if (n_local) *n_local = (int64_t)c->l2s.h_kf.size();
+  return LC_OK;
+}
+
+LC_API int32_t lc_l2_db_clear(lc_ctx* c) {
+  if (!c) return LC_ERR_INVALID;
+  LC_GUARD_BEGIN
+  LC_CUDA(c, cudaSetDevice(c->cfg.device));
+  LC_CUDA(c, cudaStreamSynchronize(c->stream));
+  for (void* p : c->l2s.slabs) cudaFree(p);
+  c->l2s = lc_ctx::L2Store{};
+  return LC_OK;
+  LC_GUARD_END(c)
+}
+
+LC_API int32_t lc_l2_match_pair(lc_ctx* c, const void* q, int32_t nq, size_t qs, const void* t, int32_t nt, size_t ts, int32_t type,
+                                double ratio, int32_t* train_idx, float* distance, float* second, uint8_t* good, int32_t* n_good) {
+  if (!c) return LC_ERR_INVALID;
+  LC_GUARD_BEGIN
+  std::vector<uint8_t> qu, tu;
+  LC_TRY(l2_to_u8(c, q, nq, qs, type, qu));
+  LC_TRY(l2_to_u8(c, t, nt, ts, type, tu));
+  if (n_good) *n_good = 0;
+  if (nq == 0) return LC_OK;
+  if (nt == 0) {  // knnMatch returns empty neighbour lists: nothing survives
+    for (int32_t i = 0; i < nq; ++i) {
+      if (train_idx) train_idx[i] = -1;
+      if (distance) distance[i] = -1.f;
+      if (second) second[i] = -1.f;
+      if (good) good[i] = 0;
+    }
+    return LC_OK;
+  }
+  LC_CUDA(c, cudaSetDevice(c->cfg.device));
+  timing_begin(c);
+  const size_t tn_off = ((size_t)nq * 4 + 255) & ~size_t(255);  // d_l2norm: query norms, then train norms
+  LC_TRY(ensure(c, c->d_l2norm, tn_off + (size_t)nt * 4));     // grow once: the two stagings below must not reallocate it
+  LC_TRY(l2_stage(c, c->d_l2q, 0, qu, nq));
+  LC_TRY(l2_stage(c, c->d_l2t, tn_off, tu, nt));
+  // device outputs: idx[nq] d1[nq] d2[nq] result(16 B) good[nq]
+  const size_t o_d1 = (size_t)nq * 4, o_d2 = o_d1 * 2, o_res = o_d1 * 3, o_good = o_res + 16, bytes = o_good + (size_t)nq;
+  LC_TRY(ensure(c, c->d_l2out, bytes));
+  LC_TRY(ensure_pin_down(c, bytes));
+  uint8_t* d = (uint8_t*)c->d_l2out.p;
+  struct {
+    l2::L2Kf kf;
+    l2::L2Frame fr;
+  } h;
+  h.kf = l2::L2Kf{(const uint4*)c->d_l2t.p, (const uint32_t*)((const uint8_t*)c->d_l2norm.p + tn_off), nt, 0};
+  h.fr = l2::L2Frame{(const uint4*)c->d_l2q.p, (const uint32_t*)c->d_l2norm.p, nq, 0, (int32_t*)d, (int32_t*)(d + o_d1), (int32_t*)(d + o_d2), d + o_good};
+  LC_TRY(ensure(c, c->d_l2frames, sizeof h));
+  LC_CUDA(c, cudaMemcpyAsync(c->d_l2frames.p, &h, sizeof h, cudaMemcpyHostToDevice, c->stream));
+  LC_CUDA(c, cudaEventRecord(c->ev[1], c->stream));
+  const l2::L2Kf* d_kf = (const l2::L2Kf*)c->d_l2frames.p;
+  const l2::L2Frame* d_fr = (const l2::L2Frame*)((const uint8_t*)c->d_l2frames.p + offsetof(decltype(h), fr));
+  LC_TRY(l2_run(c, d_kf, 1, d_fr, &h.fr, 1, (l2::L2Result*)(d + o_res), l2::L2Knobs{-(1 << 30), 0, ratio}));
+  LC_CUDA(c, cudaEventRecord(c->ev[2], c->stream));
+  LC_CUDA(c, cudaMemcpyAsync(c->pin_down, d, bytes, cudaMemcpyDeviceToHost, c->stream));
+  LC_TRY(timing_end(c));
+  const uint8_t* hp = c->pin_down;
+  const int32_t *hi = (const int32_t*)hp, *h1 = (const int32_t*)(hp + o_d1), *h2 = (const int32_t*)(hp + o_d2);
+  for (int32_t i = 0; i < nq; ++i) {  // distances as cv::DMatch carries them: sqrtf of the exact squared distance
+    if (train_idx) train_idx[i] = hi[i];
+    if (distance) distance[i] = h1[i] == l2::kNoD2 ? -1.f : sqrtf((float)h1[i]);
+    if (second) second[i] = h2[i] == l2::kNoD2 ? -1.f : sqrtf((float)h2[i]);
+    if (good) good[i] = hp[o_good + i];
+  }
+  if (n_good) *n_good = ((const l2::L2Result*)(hp + o_res))->n_good;
+  return LC_OK;
+  LC_GUARD_END(c)
+}
+
+LC_API int32_t lc_l2_loop_check(lc_ctx* c, const void* q, int32_t nq, size_t qs, int32_t type, int32_t cur_id, int32_t loop_gap,
+                                double ratio, int32_t min_rows, lc_l2_result* results, int64_t cap, int64_t* n_results) {
+  if (!c) return LC_ERR_INVALID;
+  LC_GUARD_BEGIN
+  std::vector<uint8_t> qu;
+  LC_TRY(l2_to_u8(c, q, nq, qs, type, qu));
+  auto& S = c->l2s;
+  const int64_t n_kf = (int64_t)S.h_kf.size();
+  if (n_results) *n_results = n_kf;
+  if (n_kf > 0 && (!results || cap < n_kf)) return fail(c, LC_ERR_CAPACITY, "results_cap %lld < %lld", (long long)cap, (long long)n_kf);
+  if (n_kf == 0) return LC_OK;
+  LC_CUDA(c, cudaSetDevice(c->cfg.device));
+  timing_begin(c);
+  if (S.synced != S.h_kf.size()) {  // the whole table again: views are appended rarely compared with rows
+    LC_TRY(ensure(c, S.d_kf, S.h_kf.size() * sizeof(l2::L2Kf)));
+    LC_CUDA(c, cudaMemcpyAsync(S.d_kf.p, S.h_kf.data(), S.h_kf.size() * sizeof(l2::L2Kf), cudaMemcpyHostToDevice, c->stream));
+    LC_CUDA(c, cudaStreamSynchronize(c->stream));
+    S.synced = S.h_kf.size();
+  }
+  LC_TRY(l2_stage(c, c->d_l2q, 0, qu, nq));
+  l2::L2Frame fr{(const uint4*)c->d_l2q.p, (const uint32_t*)c->d_l2norm.p, nq, cur_id, nullptr, nullptr, nullptr, nullptr};
+  LC_TRY(ensure(c, c->d_l2frames, sizeof fr));
+  LC_CUDA(c, cudaMemcpyAsync(c->d_l2frames.p, &fr, sizeof fr, cudaMemcpyHostToDevice, c->stream));
+  LC_TRY(ensure(c, c->d_l2res, (size_t)n_kf * sizeof(l2::L2Result)));
+  LC_TRY(ensure_pin_down(c, (size_t)n_kf * sizeof(l2::L2Result)));
+  LC_CUDA(c, cudaEventRecord(c->ev[1], c->stream));
+  LC_TRY(l2_run(c, (const l2::L2Kf*)S.d_kf.p, (int)n_kf, (const l2::L2Frame*)c->d_l2frames.p, &fr, 1, (l2::L2Result*)c->d_l2res.p,
+                l2::L2Knobs{loop_gap, min_rows, ratio}));
+  LC_CUDA(c, cudaEventRecord(c->ev[2], c->stream));
+  LC_CUDA(c, cudaMemcpyAsync(c->pin_down, c->d_l2res.p, (size_t)n_kf * sizeof(l2::L2Result), cudaMemcpyDeviceToHost, c->stream));
+  LC_TRY(timing_end(c));
+  static_assert(sizeof(lc_l2_result) == sizeof(l2::L2Result), "record layouts differ");
+  memcpy(results, c->pin_down, (size_t)n_kf * sizeof(lc_l2_result));
+  return LC_OK;
   LC_GUARD_END(c)
 }
 

@@ -1,0 +1,118 @@
+"""GPU parity of the shipped pipeline's SIFT / L2 matcher (lc_l2_*: knnMatch(k = 2) + Lowe ratio, reference
+src/main.cpp:509-534 and its loop search :1375-1392) against the committed cv2 fixtures (tests/golden/l2_golden.npz)
+and the CPU oracle (oracle/l2_oracle.c) - bit-exact: indices, float32 distances, ratio decisions, counts."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import l2_oracle
+
+pytestmark = pytest.mark.gpu
+
+GOLD = np.load(os.path.join(os.path.dirname(__file__), "golden", "l2_golden.npz"))
+PAIRS = sorted({k.split("/")[1] for k in GOLD.files if k.startswith("pair/")})
+
+
+@pytest.fixture(scope="module")
+def lc():
+    import slam_loop_closing_b200 as m
+    return m
+
+
+def _check_pair(r, want):
+    np.testing.assert_array_equal(r["train_idx"], want["train_idx"])
+    has1 = want["train_idx"] >= 0
+    np.testing.assert_array_equal(r["distance"][has1], want["distance"][has1])
+    np.testing.assert_array_equal(r["good"], want["good"])
+    assert r["n_good"] == int(np.sum(want["good"]))
+
+
+@pytest.mark.parametrize("name", PAIRS)
+def test_l2_match_pair_equals_golden(lc, name):
+    q, t = GOLD[f"pair/{name}/q"], GOLD[f"pair/{name}/t"]
+    with lc.Context() as c:
+        for ratio in (0.75, 0.7):
+            r = c.l2_match_pair(q, t, ratio)
+            want = dict(train_idx=GOLD[f"pair/{name}/train_idx"], distance=GOLD[f"pair/{name}/distance"],
+                        good=GOLD[f"pair/{name}/good_{ratio}"])
+            _check_pair(r, want)
+            has2 = GOLD[f"pair/{name}/second"] >= 0
+            np.testing.assert_array_equal(r["second"][has2], GOLD[f"pair/{name}/second"][has2])
+            assert (r["second"][~has2] == -1).all()
+        rf = c.l2_match_pair(q.astype(np.float32), t.astype(np.float32), 0.7)  # CV_32F rows, as cv::SIFT hands them out
+        np.testing.assert_array_equal(rf["train_idx"], r["train_idx"])
+        np.testing.assert_array_equal(rf["distance"], r["distance"])
+
+
+def _loop_case():
+    n = GOLD["loop/n"]
+    offs = np.concatenate([[0], np.cumsum(n)])
+    descs = [GOLD["loop/rows"][offs[i]:offs[i + 1]] for i in range(len(n))]
+    gap, min_rows, ratio = GOLD["loop/params"]
+    return descs, int(gap), int(min_rows), float(ratio)
+
+
+def test_l2_sift_loop_sequence_equals_golden(lc):
+    """real cv2.SIFT descriptors of a synthetic closed-loop sequence: every (curr, past <= curr - gap) pair the loop
+    search of src/main.cpp:1378-1392 visits, match counts as OpenCV gives them."""
+    descs, gap, min_rows, ratio = _loop_case()
+    want = GOLD["loop/n_good"]
+    with lc.Context() as c:
+        for curr, d in enumerate(descs):
+            assert c.l2_db_append(curr, d.astype(np.float32)) == curr
+            res = c.l2_loop_check(d, curr, gap, ratio, min_rows)
+            np.testing.assert_array_equal(res["n_good"], want[curr, :curr + 1])
+            np.testing.assert_array_equal(res["frame_id"], np.arange(curr + 1))
+        r = c.l2_match_pair(descs[-1], descs[0], ratio)
+        _check_pair(r, dict(train_idx=GOLD["loop/last_vs_first/train_idx"], distance=GOLD["loop/last_vs_first/distance"],
+                            good=GOLD["loop/last_vs_first/good"]))
+        c.l2_db_clear()
+        assert c.l2_db_size()["keyframes"] == 0 and len(c.l2_loop_check(descs[0], 5, 1)) == 0
+
+
+@pytest.mark.parametrize("nq,nt", [(1, 2), (127, 129), (128, 128), (1025, 300), (4000, 4000), (2500, 1)])
+def test_l2_pair_shapes_vs_oracle(lc, nq, nt):
+    rng = np.random.default_rng(nq * 7 + nt)
+    q = rng.integers(0, 256, (nq, 128)).astype(np.uint8)
+    t = rng.integers(0, 256, (nt, 128)).astype(np.uint8)
+    if nt > 40 and nq > 20:  # exact copies and duplicates: zero distances, ties on the train index
+        t[7], t[33], t[34] = q[3], q[3], q[10]
+    with lc.Context() as c:
+        r = c.l2_match_pair(q, t, 0.8)
+    w = l2_oracle.match_features(q, t, 0.8, nthreads=16)
+    np.testing.assert_array_equal(r["train_idx"], w["train_idx"])
+    np.testing.assert_array_equal(r["distance"], w["distance"])
+    np.testing.assert_array_equal(r["good"], w["good"])
+    assert r["n_good"] == w["n_good"]
+
+
+def test_l2_loop_check_many_views_vs_oracle(lc):
+    """a machine's worth of views (ragged, some below min_rows, some too recent) against the oracle"""
+    rng = np.random.default_rng(5)
+    q = rng.integers(0, 200, (1500, 128)).astype(np.uint8)
+    views = []
+    for k in range(220):
+        n = int(rng.integers(90, 400))
+        v = rng.integers(0, 200, (n, 128)).astype(np.uint8)
+        if k % 9 == 0:  # a view that really overlaps the query
+            m = min(n, 300)
+            v[:m] = np.clip(q[:m].astype(np.int32) + rng.integers(-2, 3, (m, 128)), 0, 255).astype(np.uint8)
+        views.append(v)
+    with lc.Context() as c:
+        for k, v in enumerate(views):
+            c.l2_db_append(k, v)
+        res = c.l2_loop_check(q, 230, 20, 0.7, 100)
+    want = l2_oracle.loop_check(q, views, list(range(220)), 230, 20, 0.7, 100, nthreads=16)
+    np.testing.assert_array_equal(res, want)
+    big = np.array([len(v) >= 100 for v in views])
+    assert (res["n_good"][:211][big[:211]] >= 0).all() and (res["n_good"][~big] == -1).all() and (res["n_good"][211:] == -1).all()
+    assert (res["n_good"][:211:9][big[:211:9]] > 100).all()  # the overlapping views stand out
+
+
+def test_l2_rejects_non_sift_values(lc):
+    with lc.Context() as c:
+        with pytest.raises(lc.LcError):
+            c.l2_db_append(0, np.full((3, 128), 0.5, np.float32))
+        with pytest.raises(lc.LcError):
+            c.l2_match_pair(np.full((3, 128), 300.0, np.float32), np.zeros((3, 128), np.float32))
