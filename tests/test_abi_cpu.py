@@ -55,6 +55,24 @@ def test_no_cpu_fallback_without_gpu():
         m.LoopClosingSystem()
 
 
+def test_plain_c_client_compiles_links_and_runs(tmp_path):
+    """include/lc_abi.h is valid C99 and the library is usable from plain C (examples/abi_client.c): on a machine
+    without a B200 the client reports lc_create's error and exits 0; on the GPU box it finds its planted loop."""
+    import shutil
+    import subprocess
+    import slam_loop_closing_b200 as m
+    if not shutil.which("gcc"):
+        pytest.skip("gcc not found")
+    lib = m.library_path()
+    exe = str(tmp_path / "abi_client")
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Werror", "-pedantic", "-I", os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "examples", "abi_client.c"), lib, "-Wl,-rpath," + os.path.dirname(lib), "-o", exe])
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "liblc_b200 ABI 1" in r.stdout
+    assert ("no CPU fallback" in r.stdout) or ("keyframe 7 recognised with all matches" in r.stdout), r.stdout
+
+
 def test_product_does_not_import_oracle():
     """A product path that routes through the oracle voids parity: grep the package for it."""
     pkg = os.path.join(ROOT, "slam_loop_closing_b200")

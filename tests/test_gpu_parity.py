@@ -339,6 +339,21 @@ def test_loop_check_begin_end_overlaps_host_work(lc):
         assert best2 is None and len(res2) == 600
 
 
+def test_plain_c_client_finds_its_loop(lc, tmp_path):
+    """examples/abi_client.c: the C ABI driven from plain C99 - no Python, torch or OpenCV between caller and library."""
+    import os
+    import shutil
+    import subprocess
+    if not shutil.which("gcc"):
+        pytest.skip("gcc not found")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    lib, exe = lc.library_path(), str(tmp_path / "abi_client")
+    subprocess.check_call(["gcc", "-std=c99", "-I", os.path.join(root, "include"), os.path.join(root, "examples", "abi_client.c"),
+                           lib, "-Wl,-rpath," + os.path.dirname(lib), "-o", exe])
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0 and "keyframe 7 recognised with all matches" in r.stdout, r.stdout + r.stderr
+
+
 def test_sharded_contexts_merge_equals_single(lc):
     """two shard contexts on one GPU: merged per-keyframe records and min-merged best == unsharded."""
     p = Params(loop_threshold=0.15, min_loop_gap=10)
