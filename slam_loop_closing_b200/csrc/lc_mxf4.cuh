@@ -12,18 +12,21 @@
 // the tie-break MMA step of lc_tensor.cuh (1/5 of the MMA time here) and leaves a plain FMNMX3 fold as epilogue.
 //
 // Shape (all measured on B200):
-//   * M = 128 queries x N = 224 train rows x K = 64 per MMA, 4 MMAs per tile.  One mxf4 MMA costs
-//     max(111, N / 2) cycles with both operands in shared memory, so N = 224 is the smallest full-rate tile; two
-//     224-column f32 accumulators + the scale-factor cells fill TMEM's 512 columns.
+//   * M = 128 queries x N = 224 train rows x K = 64 per MMA, 4 MMAs per tile = 448 cycles.  One mxf4 MMA costs N / 2
+//     cycles for N >= 128 with both operands in shared memory; two 224-column f32 accumulators + the scale-factor
+//     cells fill TMEM's 512 columns, and the long tile amortises the per-tile hand-offs best (three 128-column stages
+//     were measured: not faster).
 //   * A (queries) is RESIDENT: one CTA owns up to 1024 queries = 8 tiles x 16 KiB (a packed E2M1 row of 256 values is
 //     128 B = one SWIZZLE_128B row), written once by expand_queries_fp4_kernel and pulled in with bulk copies.
 //   * B (keyframe rows) is expanded IN the kernel from the 32-byte rows in HBM (the store stays 32 B/row): 4 expander
 //     warps, 9 ALU ops per 32 descriptor bits (PRMT as a 2-bit -> byte lookup), 3 stages of 28 KiB.  A B tile is
 //     reused by all resident A tiles.
-//   * 8 epilogue warps (TMEM lane quadrant x column half) read the accumulator with tcgen05.ld (>= 341 B/clk/SM
-//     measured next to full-rate MMAs; 256 B/clk/SM are needed) and fold 112 columns into one running maximum per
-//     query with FMNMX3: 448 warp instructions per tile, a quarter of the SM's issue slots - with everything else
-//     the kernel is issue-bound as much as tensor-bound, so per-tile overhead instructions are kept minimal.
+//   * 8 epilogue warps (TMEM lane quadrant x column half) read the accumulator with tcgen05.ld (700 B/clk/SM measured
+//     next to full-rate MMAs; 256 B/clk/SM are needed) and fold 112 columns into one running maximum per query with
+//     FMNMX3: 448 warp instructions per tile on the half-rate alu pipe = half of a tile's cycles per SM sub-partition,
+//     a quarter of the SM's issue slots.  With everything else the kernel is issue-bound as much as tensor-bound, so
+//     per-tile overhead instructions are kept minimal; the drain (wake-up + load latency + fold, ~490 cycles per tile)
+//     is what keeps the tensor pipe at 91 % (DESIGN.md 4c lists the variants that were measured and did not help).
 //   * one MMA issuer warp; mbarriers + tcgen05.commit connect the three roles.
 // Output: scratch[(frame * kc + (k - k0)) * stride + q] = min distance (u16), plain stores, every compared (frame, k, q)
 // written exactly once - no memset, no atomics; per query, (min distance << 32 | first keyframe at that distance) is
