@@ -8,7 +8,8 @@
 // cv::BFMatcher member `matcher_` (include/loop_closing.hpp:73) is replaced by an lc_ctx*.
 //
 // This header needs OpenCV's C++ headers (cv::Mat, cv::DMatch).  They are not installed in the build
-// image of this repo, so it is not compiled by the test-suite; the executable proof of the same
+// image of this repo: the test-suite compiles it against a minimal stand-in for those two types
+// (tests/stubs/opencv2/), which checks every call against include/lc_abi.h; the executable proof of the same
 // drop-in is slam_loop_closing_b200/loop_closing.py, which binds the same C ABI.
 #pragma once
 
@@ -83,11 +84,103 @@ class HammingMatcher {
     return out;
   }
 
+  // detectLoops split in two, so that processFrame can detect the next image's features while the GPU scans the store:
+  // beginDetectLoops copies the descriptors and returns at once, finishDetectLoops waits and applies README.md:121-126
+  void beginDetectLoops(int current_frame_id, const cv::Mat& current_descriptors) {
+    check(current_descriptors);
+    pending_nq_ = current_descriptors.rows;
+    pending_id_ = current_frame_id;
+    ok(lc_loop_check_begin(ctx_, current_descriptors.data, current_descriptors.rows,
+                           current_descriptors.rows ? current_descriptors.step[0] : 32, current_frame_id, 0));
+  }
+  std::vector<LoopCandidate> finishDetectLoops() {
+    int64_t n_kf = 0, n = 0, n_out = 0;
+    ok(lc_db_size(ctx_, &n_kf, nullptr, nullptr, nullptr));
+    std::vector<lc_kf_result> rec(static_cast<size_t>(n_kf));
+    ok(lc_loop_check_end(ctx_, rec.data(), n_kf, &n, nullptr));
+    std::vector<LoopCandidate> out(static_cast<size_t>(n));
+    ok(lc_select_candidates(ctx_, rec.data(), n, pending_nq_, pending_id_, reinterpret_cast<lc_loop_candidate*>(out.data()), n, &n_out));
+    out.resize(static_cast<size_t>(n_out));
+    return out;
+  }
+
+  // matchFeatures(current, frames_[k]) for the loop candidates in ONE call: the DMatch lists estimatePose /
+  // triangulatePoints (include/loop_closing.hpp:43-53) verify a loop with.  kf_index[i] = position of the matched frame
+  // in frames_ (the store shares its insertion order).
+  std::vector<std::vector<cv::DMatch>> matchCandidates(const cv::Mat& current_descriptors, const std::vector<int64_t>& kf_index) {
+    check(current_descriptors);
+    const int nq = current_descriptors.rows, n_sel = static_cast<int>(kf_index.size());
+    std::vector<lc_match> m(static_cast<size_t>(nq) * kf_index.size());
+    std::vector<int64_t> offs(kf_index.size() + 1);
+    ok(lc_match_keyframes(ctx_, current_descriptors.data, nq, nq ? current_descriptors.step[0] : 32, n_sel, kf_index.data(), m.data(),
+                          static_cast<int64_t>(m.size()), offs.data(), nullptr));
+    std::vector<std::vector<cv::DMatch>> out(kf_index.size());
+    for (size_t i = 0; i < kf_index.size(); ++i)
+      for (int64_t j = offs[i]; j < offs[i + 1]; ++j)
+        out[i].emplace_back(m[j].query_idx, m[j].train_idx, 0, static_cast<float>(m[j].distance));
+    return out;
+  }
+
   lc_ctx* handle() { return ctx_; }
 
  private:
   static void check(const cv::Mat& d) {
     if (!d.empty() && (d.type() != CV_8UC1 || d.cols != LC_DESC_BYTES)) throw std::invalid_argument("descriptors must be CV_8UC1 n x 32");
+  }
+  void ok(int32_t rc) {
+    if (rc != LC_OK) throw std::runtime_error(lc_last_error(ctx_));
+  }
+  lc_ctx* ctx_ = nullptr;
+  int pending_nq_ = 0, pending_id_ = 0;
+};
+
+// The SHIPPED pipeline (src/main.cpp): matchFeatures (:509-534) and the matching step of its loop search (:1378-1392)
+class SiftMatcher {
+ public:
+  explicit SiftMatcher(int device = 0) {
+    lc_config cfg;
+    lc_default_config(&cfg);
+    cfg.device = device;
+    if (lc_create(&cfg, &ctx_) != LC_OK) throw std::runtime_error(lc_last_error(nullptr));
+  }
+  ~SiftMatcher() { lc_destroy(ctx_); }
+  SiftMatcher(const SiftMatcher&) = delete;
+  SiftMatcher& operator=(const SiftMatcher&) = delete;
+
+  // void matchFeatures(desc1, desc2, goodMatches, ratio): knnMatch(k = 2) + Lowe's ratio test
+  void matchFeatures(const cv::Mat& desc1, const cv::Mat& desc2, std::vector<cv::DMatch>& goodMatches, double ratio = 0.75) {
+    goodMatches.clear();
+    const int nq = desc1.rows;
+    std::vector<int32_t> idx(nq);
+    std::vector<float> dist(nq);
+    std::vector<uint8_t> good(nq);
+    int32_t n_good = 0;
+    ok(lc_l2_match_pair(ctx_, desc1.data, nq, nq ? desc1.step[0] : 512, desc2.data, desc2.rows, desc2.rows ? desc2.step[0] : 512,
+                        type_of(desc1), ratio, idx.data(), dist.data(), nullptr, good.data(), &n_good));
+    goodMatches.reserve(n_good);
+    for (int i = 0; i < nq; ++i)
+      if (good[i]) goodMatches.emplace_back(i, idx[i], 0, dist[i]);
+  }
+  // allDescriptors.push_back(desc) of the shipped main(): the view joins the device-resident store
+  void addView(int view, const cv::Mat& desc) {
+    ok(lc_l2_db_append(ctx_, view, desc.data, desc.rows, desc.rows ? desc.step[0] : 512, type_of(desc), nullptr));
+  }
+  // matches.size() of (curr, past) for every stored view past <= curr - loopGap, -1 where main.cpp:1384 skips the pair
+  std::vector<lc_l2_result> loopMatchCounts(const cv::Mat& curr_desc, int curr, int loopGap, double ratio = 0.7, int min_rows = 100) {
+    int64_t n_local = 0, n = 0;
+    ok(lc_l2_db_size(ctx_, nullptr, &n_local));
+    std::vector<lc_l2_result> out(static_cast<size_t>(n_local));
+    ok(lc_l2_loop_check(ctx_, curr_desc.data, curr_desc.rows, curr_desc.rows ? curr_desc.step[0] : 512, type_of(curr_desc), curr, loopGap,
+                        ratio, min_rows, out.data(), n_local, &n));
+    out.resize(static_cast<size_t>(n));
+    return out;
+  }
+
+ private:
+  static int32_t type_of(const cv::Mat& d) {
+    if (d.empty() || (d.type() == CV_32FC1 && d.cols == LC_L2_DIMS)) return LC_DESC_F32;
+    if (d.type() == CV_8UC1 && d.cols == LC_L2_DIMS) return LC_DESC_U8;
+    throw std::invalid_argument("SIFT descriptors must be CV_32F or CV_8U, n x 128");
   }
   void ok(int32_t rc) {
     if (rc != LC_OK) throw std::runtime_error(lc_last_error(ctx_));

@@ -73,6 +73,22 @@ def test_plain_c_client_compiles_links_and_runs(tmp_path):
     assert ("no CPU fallback" in r.stdout) or ("keyframe 7 recognised with all matches" in r.stdout), r.stdout
 
 
+def test_cpp_adapter_compiles_against_the_abi(tmp_path):
+    """include/loop_closing_b200.hpp (the adapter a maintainer of the reference would add) compiles and links: OpenCV's
+    C++ headers are not in the image, so cv::Mat / cv::DMatch come from a minimal stand-in (tests/stubs/opencv2)."""
+    import shutil
+    import subprocess
+    import slam_loop_closing_b200 as m
+    if not shutil.which("g++"):
+        pytest.skip("g++ not found")
+    lib = m.library_path()
+    exe = str(tmp_path / "adapter_check")
+    subprocess.check_call(["g++", "-std=c++17", "-Wall", "-Werror", "-I", os.path.join(ROOT, "tests", "stubs"),
+                           "-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "tests", "stubs", "adapter_check.cpp"), lib,
+                           "-Wl,-rpath," + os.path.dirname(lib), "-o", exe])
+    assert subprocess.run([exe], timeout=120).returncode == 0
+
+
 def test_product_does_not_import_oracle():
     """A product path that routes through the oracle voids parity: grep the package for it."""
     pkg = os.path.join(ROOT, "slam_loop_closing_b200")
