@@ -383,7 +383,7 @@ int run_match(lc_ctx* c, cudaStream_t st, const KfEntry* d_kfs, int n_kf, int ma
           used += ns[i];
         }
         // hand the rounding remainder to the blocks whose CTAs carry the most work
-        for (long long left = total - used; left > 0; --left) {
+        for (long long left = n_ab <= 256 ? total - used : 0; left > 0; --left) {  // (quadratic in the block count)
           int arg = -1;
           double w = -1;
           for (int i = 0; i < n_ab; ++i) {
