@@ -149,9 +149,13 @@ class Context:
             raise LcError(rc, self._lib.lc_last_error(None).decode())
 
     def close(self):
-        if getattr(self, "_h", None) is not None and self._h.value:
-            self._lib.lc_destroy(self._h)
-            self._h = _vp()
+        h = getattr(self, "_h", None)
+        if h is not None and h.value:
+            try:
+                self._lib.lc_destroy(h)
+            except TypeError:  # interpreter shutdown: ctypes has already torn the function object down
+                pass
+            self._h = None
 
     __del__ = close
 
