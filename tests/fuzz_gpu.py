@@ -1,0 +1,65 @@
+"""Randomised parity soak: random shapes / kernels / knobs through the C ABI against the CPU oracle, for a time budget.
+   python tests/fuzz_gpu.py [seconds] [seed]      (tests/test_gpu_fuzz.py runs a short one in the GPU suite)"""
+import os
+import sys
+import time
+import numpy as np
+_HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(_HERE))
+sys.path.insert(0, _HERE)
+import datagen
+import slam_loop_closing_b200 as lc
+from oracle import c_oracle, l2_oracle
+from oracle.params import Params
+
+
+
+def soak(budget, seed):
+    rng = np.random.default_rng(seed)
+    t0, cases = time.time(), 0
+    while time.time() - t0 < budget:
+        cases += _one_case(rng, cases)
+    return cases, time.time() - t0
+
+
+def _one_case(rng, cases):
+    if True:
+        kernel = int(rng.choice([0, 2, 3, 4]))
+        n_kf = int(rng.integers(1, 500))
+        max_rows = int(rng.choice([40, 250, 700, 2300]))
+        p = Params(loop_threshold=0.15, min_loop_gap=int(rng.integers(0, 40)), filter_floor=int(rng.choice([0, 30])),
+                   filter_strict=bool(rng.integers(0, 2)), gap_strict=bool(rng.integers(0, 2)))
+        gen = datagen.low_entropy if rng.integers(0, 2) else datagen.uniform
+        kfs = [gen(int(rng.integers(0, max_rows)), int(rng.integers(1 << 30))) for _ in range(n_kf)]
+        fids = np.sort(rng.choice(np.arange(n_kf * 2), n_kf, replace=False)).tolist()
+        F = int(rng.choice([1, 1, 2, 5]))
+        qs = [gen(int(rng.integers(0, 2600)), int(rng.integers(1 << 30))) for _ in range(F)]
+        if len(qs[0]) and n_kf > 3 and len(kfs[2]):  # plant a noisy copy so that n_good is not trivial
+            kfs[2] = datagen.noisy_copy(qs[0], 5, p=0.05, n=max(len(kfs[2]), 1))
+        curs = [int(rng.integers(0, n_kf * 2 + 50)) for _ in range(F)]
+        with lc.Context(kernel=kernel, loop_threshold=p.loop_threshold, min_loop_gap=p.min_loop_gap, filter_floor=p.filter_floor,
+                        filter_strict=p.filter_strict, gap_strict=p.gap_strict) as c:
+            c.db_append_many(fids, kfs)
+            res, best = c.loop_check_batch(qs, curs)
+            path = c.last_timing().path
+        db = np.concatenate(kfs) if n_kf else np.zeros((0, 32), np.uint8)
+        for f in range(F):
+            w_res, w_best = c_oracle.loop_check(qs[f], db, [len(k) for k in kfs], fids, curs[f], p, nthreads=16)
+            assert np.array_equal(res[f], w_res), (cases, kernel, path, "records")
+            assert np.array_equal(best[f], w_best), (cases, kernel, path, "best")
+        if cases % 7 == 0:  # the SIFT / L2 path
+            a = rng.integers(0, 256, (int(rng.integers(1, 1500)), 128)).astype(np.uint8)
+            b = rng.integers(0, 256, (int(rng.integers(1, 1500)), 128)).astype(np.uint8)
+            if rng.integers(0, 2):
+                a, b = (a // 64) * 40, (b // 64) * 40  # few distinct values: many equal distances
+            with lc.Context() as c:
+                g = c.l2_match_pair(a, b, 0.8)
+            w = l2_oracle.match_features(a, b, 0.8, nthreads=16)
+            assert np.array_equal(g["train_idx"], w["train_idx"]) and np.array_equal(g["distance"], w["distance"]) and \
+                np.array_equal(g["good"], w["good"]), (cases, "l2")
+    return 1
+
+
+if __name__ == "__main__":
+    n, dt = soak(float(sys.argv[1]) if len(sys.argv) > 1 else 120.0, int(sys.argv[2]) if len(sys.argv) > 2 else 1)
+    print(f"fuzz ok: {n} random cases in {dt:.0f} s, all bit-exact")
