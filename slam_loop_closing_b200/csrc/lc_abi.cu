@@ -62,6 +62,7 @@ struct lc_ctx {
   size_t d_kf_synced = 0;
   int64_t g_kf = 0, g_rows = 0, l_rows = 0;
   int32_t max_n_local = 0;
+  int64_t n_partial_kf = 0;  // local keyframes whose last FP4 tile is not full width (lc_mxf4.cuh: full_tiles_only)
 
   // ---- staging / work buffers
   uint8_t* pin_up = nullptr;  // 2 x kPinHalfBytes
@@ -258,6 +259,7 @@ int store_append(lc_ctx* c, int32_t frame_id, const uint8_t* desc, int32_t n, si
     c->h_kf_global.push_back(k);
     c->l_rows += n;
     c->max_n_local = std::max(c->max_n_local, n);
+    c->n_partial_kf += (n > 0 && !fx::full_tiles_only(n)) ? 1 : 0;
   }
   if (kf_index) *kf_index = k;
   c->g_kf += 1;
@@ -333,7 +335,7 @@ struct PairOut {  // optional per-query outputs of the pair API (device pointers
 // h_frames mirrors d_frames (needed for nq).  max_rows = max n over the keyframes.
 int run_match(lc_ctx* c, cudaStream_t st, const KfEntry* d_kfs, int n_kf, int max_rows, const QFrame* d_frames,
               const QFrame* h_frames, int n_frames, lc_kf_result* d_results, const PairOut& po, Knobs kb,
-              bool force_split) {
+              bool force_split, bool full_tiles = false) {
   const long long n_items = (long long)n_kf * n_frames;
   if (n_items == 0) return LC_OK;
   if (n_items > 0x7fffffffll) return fail(c, LC_ERR_INVALID, "too many (frame, keyframe) items: %lld", n_items);
@@ -430,7 +432,8 @@ int run_match(lc_ctx* c, cudaStream_t st, const KfEntry* d_kfs, int n_kf, int ma
       LC_CUDA(c, cudaGetLastError());
       if (!c->smem_attr_set) {  // per device, so per context
         LC_CUDA(c, cudaFuncSetAttribute(tc::tensor_match_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kSmemAlloc));
-        LC_CUDA(c, cudaFuncSetAttribute(fx::mxf4_match_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, fx::kSmemAlloc));
+        LC_CUDA(c, cudaFuncSetAttribute(fx::mxf4_match_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, fx::kSmemAlloc));
+        LC_CUDA(c, cudaFuncSetAttribute(fx::mxf4_match_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, fx::kSmemAlloc));
         c->smem_attr_set = true;
       }
       LC_TRY(ensure(c, c->d_scratch, (size_t)kc_max * n_frames * stride * elem));
@@ -442,8 +445,13 @@ int run_match(lc_ctx* c, cudaStream_t st, const KfEntry* d_kfs, int n_kf, int ma
           // every compared (frame, keyframe, query) distance is stored exactly once: no scratch initialisation
           {
             MatchTimer mt(c, st);
-            fx::mxf4_match_kernel<<<(unsigned)work.size(), fx::kThreads, fx::kSmemAlloc, st>>>(
-                d_kfs, k0, kc, d_frames, (const fx::ABlock*)d_blocks, d_work, (uint16_t*)c->d_scratch.p, stride, kb);
+            // specialisation of an issue-bound kernel: full-width train tiles only
+            auto launch = [&](auto kern) {
+              kern<<<(unsigned)work.size(), fx::kThreads, fx::kSmemAlloc, st>>>(d_kfs, k0, kc, d_frames, (const fx::ABlock*)d_blocks, d_work,
+                                                                               (uint16_t*)c->d_scratch.p, stride, kb);
+            };
+            if (full_tiles) launch(fx::mxf4_match_kernel<true>);
+            else launch(fx::mxf4_match_kernel<false>);
           }
           LC_CUDA(c, cudaGetLastError());
           fx::finalize_dist_kernel<<<(kc * n_frames + fx::kFinWarps - 1) / fx::kFinWarps, fx::kFinWarps * 32, 0, st>>>(
@@ -579,7 +587,7 @@ int loop_check_device_impl(lc_ctx* c, cudaStream_t st, int n_frames, const void*
   // pageable source: the runtime stages it before returning, so `hf` may die with this frame
   LC_CUDA(c, cudaMemcpyAsync(c->d_frames.p, hf.data(), hf.size() * sizeof(QFrame), cudaMemcpyHostToDevice, st));
   return run_match(c, st, (const KfEntry*)c->d_kf.p, n_kf, c->max_n_local, (const QFrame*)c->d_frames.p, hf.data(), n_frames,
-                   d_results, PairOut{}, knobs_of(c->cfg), false);
+                   d_results, PairOut{}, knobs_of(c->cfg), false, c->n_partial_kf == 0);
 }
 
 int pair_device_impl(lc_ctx* c, cudaStream_t st, const void* d_q, int nq, const KfEntry& train, const PairOut& po) {
@@ -845,6 +853,7 @@ LC_API int32_t lc_db_clear(lc_ctx* c) {
   c->d_kf_synced = 0;
   c->g_kf = c->g_rows = c->l_rows = 0;
   c->max_n_local = 0;
+  c->n_partial_kf = 0;
   return LC_OK;
   LC_GUARD_END(c)
 }
@@ -959,6 +968,7 @@ LC_API int32_t lc_db_load(lc_ctx* c, const char* path) {
     c->h_kf_global.push_back(r.gi);
     c->l_rows += r.n;
     c->max_n_local = std::max(c->max_n_local, r.n);
+    c->n_partial_kf += (r.n > 0 && !fx::full_tiles_only(r.n)) ? 1 : 0;
   }
   fclose(f);
   if (!ok) {

@@ -214,10 +214,16 @@ __device__ __forceinline__ float drain_accumulator(uint32_t taddr, int ncols, ui
 
 // columns of a tile with `cnt` valid rows: rounded up to 32 (pad rows are copies of the last valid row, so they never
 // change a maximum) - every column half is then a whole number of 16-column loads
-__device__ __forceinline__ int tile_cols(int cnt) { return (cnt + 31) & ~31; }
+__host__ __device__ __forceinline__ int tile_cols(int cnt) { return (cnt + 31) & ~31; }
+// does a keyframe of n rows consist of full-width tiles only?
+inline bool full_tiles_only(int n) { return n > 0 && tile_cols(n - (n - 1) / kTN * kTN) == kTN; }
 
 // ---------------------------------------------------------------- the kernel
 // One CTA per CtaWork entry: query block `ablock` against keyframes k0 + slot, k0 + slot + n_slots, ...
+// FULL: every B tile of every keyframe of the launch spans all 224 columns (true for the usual 2000-row keyframes: 8 x 224 +
+// 208 -> 224 with pad rows); the host knows, and the per-tile column arithmetic and its branches drop out of an
+// instruction stream that is the kernel's bottleneck.
+template <bool FULL>
 __global__ void __launch_bounds__(kThreads, 1)
     mxf4_match_kernel(const KfEntry* __restrict__ kfs, int k0, int kc, const QFrame* __restrict__ frames,
                       const ABlock* __restrict__ blocks, const CtaWork* __restrict__ work, uint16_t* __restrict__ scratch,
@@ -293,15 +299,15 @@ __global__ void __launch_bounds__(kThreads, 1)
       const KfEntry kf = kfs[k];
       if (!kf_eligible(fr.cur_id, kf.frame_id, kb) || kf.n <= 0) continue;
       for (int row0 = 0; row0 < kf.n; row0 += kTN) {
-        const uint32_t idesc = instr_desc_mxf4(tile_cols(min(kTN, kf.n - row0)));
+        const uint32_t idesc = instr_desc_mxf4(FULL ? kTN : tile_cols(min(kTN, kf.n - row0)));
         const uint64_t bdesc = bdesc0 + (uint64_t)((bb * kBTileBytes) >> 4);
         mbar_wait_a(b_full + 8 * bb, (par_bfull >> bb) & 1);
         par_bfull ^= 1u << bb;
         tc_fence_after();
 #pragma unroll 1
         for (int m = 0; m < m_tiles; ++m, ++t) {
-          const uint32_t st = t & 1;
-          mbar_wait_a(acc_empty + 8 * st, ((t >> 1) & 1) ^ 1);
+          const uint32_t st = t & 1u, par = (t >> 1) & 1u;
+          mbar_wait_a(acc_empty + 8 * st, par ^ 1);
           tc_fence_after();
           if (leader) {
             const uint32_t d = tmem_base + st * kAccStride;
@@ -348,7 +354,7 @@ __global__ void __launch_bounds__(kThreads, 1)
 #pragma unroll
           for (int i = 0; i < kPairsPerExpThread; ++i) bits[i] = __ldg(pairs + (size_t)(row0 + min(r0 + 32 * i, cnt - 1)) * 4 + wp);
         }
-        const int rows_used = tile_cols(cnt);
+        const int rows_used = FULL ? kTN : tile_cols(cnt);
         mbar_wait_a(b_empty + 8 * bb, (par_bempty >> bb) & 1);
         par_bempty ^= 1u << bb;
         uint8_t* tile = sB + bb * kBTileBytes;
@@ -383,12 +389,12 @@ __global__ void __launch_bounds__(kThreads, 1)
 #pragma unroll
       for (int m = 0; m < kQTilesPerCta; ++m) best[m] = -1024.f;
       for (int row0 = 0; row0 < kf.n; row0 += kTN) {
-        const int hcols = tile_cols(min(kTN, kf.n - row0)) >> 1;  // columns per half: a multiple of 16
+        const int hcols = FULL ? kTN / 2 : tile_cols(min(kTN, kf.n - row0)) >> 1;  // columns per half: a multiple of 16
 #pragma unroll
         for (int m = 0; m < kQTilesPerCta; ++m) {
           if (m < m_tiles) {
-            const uint32_t st = t & 1;
-            mbar_wait_a(acc_full + 8 * st, (t >> 1) & 1);
+            const uint32_t st = t & 1u, par = (t >> 1) & 1u;
+            mbar_wait_a(acc_full + 8 * st, par);
             tc_fence_after();
             best[m] = fmaxf(best[m], drain_accumulator(tmem_rows + st * kAccStride + (uint32_t)(half * hcols), hcols, acc_empty + 8 * st));
             ++t;
