@@ -37,6 +37,8 @@ constexpr size_t kPinHalfBytes = 8u << 20;  // two pinned upload halves of 8 MiB
 constexpr int64_t kDefaultSlabRows = 8ll << 20;
 constexpr size_t kScratchBudgetBytes = 256u << 20;
 constexpr int kFusedMaxNq = kMaxThreads * 8;
+constexpr size_t kPairDirectOutBytes = 256u << 10;  // pair results up to this size are stored straight into pinned host memory
+constexpr int kPairMinSegRows = 8;  // fewest train rows a pair-kernel CTA scans
 
 struct Shape {  // launch shape for nq queries
   int rq, threads, chunks;
@@ -68,8 +70,9 @@ struct lc_ctx {
   uint8_t* pin_up = nullptr;  // 2 x kPinHalfBytes
   int pin_half = 0;
   uint8_t* pin_down = nullptr;
+  uint8_t* pin_down_dev = nullptr;  // the same buffer as the device addresses it (results stored by kernels directly)
   size_t pin_down_cap = 0;
-  DevBuf d_q, d_t, d_results, d_best, d_scratch, d_frames, d_pair, d_out, d_counter, d_qimg, d_ablocks;
+  DevBuf d_q, d_t, d_results, d_best, d_scratch, d_frames, d_pairkeys, d_paircnt, d_out, d_counter, d_qimg, d_ablocks;
 
   lc_timing timing{};
   int64_t launches = 0;
@@ -154,7 +157,8 @@ int ensure_pin_down(lc_ctx* c, size_t bytes) {
     c->pin_down_cap = 0;
   }
   size_t ncap = std::max(bytes, c->pin_down_cap * 2);
-  LC_CUDA(c, cudaMallocHost((void**)&c->pin_down, ncap));
+  LC_CUDA(c, cudaHostAlloc((void**)&c->pin_down, ncap, cudaHostAllocMapped));
+  LC_CUDA(c, cudaHostGetDevicePointer((void**)&c->pin_down_dev, c->pin_down, 0));
   c->pin_down_cap = ncap;
   return LC_OK;
 }
@@ -334,8 +338,7 @@ struct PairOut {  // optional per-query outputs of the pair API (device pointers
 // Match n_frames query frames against n_kf keyframes (device tables) on `st`.
 // h_frames mirrors d_frames (needed for nq).  max_rows = max n over the keyframes.
 int run_match(lc_ctx* c, cudaStream_t st, const KfEntry* d_kfs, int n_kf, int max_rows, const QFrame* d_frames,
-              const QFrame* h_frames, int n_frames, lc_kf_result* d_results, const PairOut& po, Knobs kb,
-              bool force_split, bool full_tiles = false) {
+              const QFrame* h_frames, int n_frames, lc_kf_result* d_results, Knobs kb, bool full_tiles) {
   const long long n_items = (long long)n_kf * n_frames;
   if (n_items == 0) return LC_OK;
   if (n_items > 0x7fffffffll) return fail(c, LC_ERR_INVALID, "too many (frame, keyframe) items: %lld", n_items);
@@ -347,7 +350,7 @@ int run_match(lc_ctx* c, cudaStream_t st, const KfEntry* d_kfs, int n_kf, int ma
   //      + arg-max (lc_tensor.cuh)
   const int kern = c->cfg.kernel;
   const bool want_fp4 = kern == LC_KERNEL_MXF4 || kern == LC_KERNEL_AUTO, want_i8 = kern == LC_KERNEL_TENSOR;
-  if ((want_fp4 || want_i8) && !force_split && max_nq > 0 && max_rows > 0) {
+  if ((want_fp4 || want_i8) && max_nq > 0 && max_rows > 0) {
     const int q_per_cta = want_fp4 ? fx::kQPerCta : tc::kQPerCta;
     const size_t img_bytes = want_fp4 ? (size_t)fx::kABytes : (size_t)tc::kABytes;
     std::vector<tc::ABlock> blocks;  // fx::ABlock has the same layout
@@ -465,7 +468,7 @@ int run_match(lc_ctx* c, cudaStream_t st, const KfEntry* d_kfs, int n_kf, int ma
           }
           LC_CUDA(c, cudaGetLastError());
           finalize_kernel<<<kc * n_frames, 256, 0, st>>>(d_kfs, n_kf, k0, kc, d_frames, (const uint32_t*)c->d_scratch.p, stride,
-                                                         d_results, po.train_idx, po.dist, po.good, po.summary, kb);
+                                                         d_results, nullptr, nullptr, nullptr, nullptr, kb);
         }
         LC_CUDA(c, cudaGetLastError());
         c->launches += 2;
@@ -492,7 +495,7 @@ int run_match(lc_ctx* c, cudaStream_t st, const KfEntry* d_kfs, int n_kf, int ma
   }
 
   // ---- whole-keyframe scan: enough items to fill every CTA slot many times over
-  if (!force_split && max_nq <= kFusedMaxNq && max_nq > 0) {
+  if (max_nq <= kFusedMaxNq && max_nq > 0) {
     const Shape sh = scan_shape(max_nq);
     const int occ = mode == MODE_POPC ? scan_occupancy<MODE_POPC>(sh.rq, sh.threads) : scan_occupancy<MODE_CSA>(sh.rq, sh.threads);
     const long long slots = (long long)c->num_sms * occ;
@@ -549,7 +552,7 @@ int run_match(lc_ctx* c, cudaStream_t st, const KfEntry* d_kfs, int n_kf, int ma
       c->timing.kernel_launches += 1;
     }
     finalize_kernel<<<nb, 256, 0, st>>>(d_kfs, n_kf, k0, kc, d_frames, (const uint32_t*)c->d_scratch.p, stride, d_results,
-                                        po.train_idx, po.dist, po.good, po.summary, kb);
+                                        nullptr, nullptr, nullptr, nullptr, kb);
     LC_CUDA(c, cudaGetLastError());
     c->launches += 1;
     c->timing.kernel_launches += 1;
@@ -587,32 +590,82 @@ int loop_check_device_impl(lc_ctx* c, cudaStream_t st, int n_frames, const void*
   // pageable source: the runtime stages it before returning, so `hf` may die with this frame
   LC_CUDA(c, cudaMemcpyAsync(c->d_frames.p, hf.data(), hf.size() * sizeof(QFrame), cudaMemcpyHostToDevice, st));
   return run_match(c, st, (const KfEntry*)c->d_kf.p, n_kf, c->max_n_local, (const QFrame*)c->d_frames.p, hf.data(), n_frames,
-                   d_results, PairOut{}, knobs_of(c->cfg), false, c->n_partial_kf == 0);
+                   d_results, knobs_of(c->cfg), c->n_partial_kf == 0);
 }
 
+// matchFeatures on device-resident rows: one launch of pair_kernel (lc_kernels.cuh); nq, nt > 0
 int pair_device_impl(lc_ctx* c, cudaStream_t st, const void* d_q, int nq, const KfEntry& train, const PairOut& po) {
-  // one temporary (frame, keyframe) item; the gap test is disabled (matchFeatures has none)
-  struct {
-    KfEntry kf;
-    QFrame fr;
-  } h;
-  h.kf = train;
-  h.kf.frame_id = 0;
-  h.kf.global_row_off = 0;
-  h.fr = QFrame{(const uint4*)d_q, nq, 0, nullptr};
-  LC_TRY(ensure(c, c->d_pair, sizeof h));
-  LC_CUDA(c, cudaMemcpyAsync(c->d_pair.p, &h, sizeof h, cudaMemcpyHostToDevice, st));
-  Knobs kb = knobs_of(c->cfg);
-  kb.min_loop_gap = -(1 << 30);
-  kb.gap_strict = 0;
-  const KfEntry* d_kf = (const KfEntry*)c->d_pair.p;
-  const QFrame* d_fr = (const QFrame*)((const uint8_t*)c->d_pair.p + offsetof(decltype(h), fr));
-  return run_match(c, st, d_kf, 1, train.n, d_fr, &h.fr, 1, nullptr, po, kb, true);
+  const int nt = train.n;
+  // keys[nq] and {ticket counter, smallest distance} rest at 0xffffffff / {0, 0xffffffff} between calls (the kernel's last CTA puts them back)
+  const size_t need = (size_t)nq * 4;
+  if (c->d_pairkeys.cap < need) {
+    LC_TRY(ensure(c, c->d_pairkeys, need));
+    LC_CUDA(c, cudaMemsetAsync(c->d_pairkeys.p, 0xff, c->d_pairkeys.cap, st));
+  }
+  if (!c->d_paircnt.p) {
+    LC_TRY(ensure(c, c->d_paircnt, 256));
+    const unsigned int idle[2] = {0u, 0xffffffffu};  // ticket counter, smallest distance
+    LC_CUDA(c, cudaMemcpyAsync(c->d_paircnt.p, idle, sizeof idle, cudaMemcpyHostToDevice, st));
+  }
+  // The launch is a whole number of waves of near-equal CTAs, two per SM: the integer pipes bound the kernel, so an SM
+  // that gets one CTA more than its neighbour sets the call's latency.  Two queries per thread measured fastest across
+  // shapes (tools/pair_shapes.cu: 4 M pairs in 12.4 us per back-to-back launch, 8.3 us of it fixed latency).
+  constexpr int kRq = 2;
+  const int threads = std::min(256, std::max(32, ((nq + 32 * kRq - 1) / (32 * kRq)) * 32));
+  const int chunks = (nq + threads * kRq - 1) / (threads * kRq);
+  const long long segs_per_wave = std::max<long long>(1, 2ll * c->num_sms / chunks);
+  const long long waves = std::max<long long>(1, (nt + kTileRows * segs_per_wave - 1) / (kTileRows * segs_per_wave));
+  const int seg = (int)std::min<long long>(kTileRows, std::max<long long>(kPairMinSegRows, (nt + waves * segs_per_wave - 1) / (waves * segs_per_wave)));
+  const long long n_seg = (nt + seg - 1) / seg;
+  if (chunks > 65535) return fail(c, LC_ERR_INVALID, "pair match: %d query rows need %d chunks (max 65535)", nq, chunks);
+  const dim3 grid((unsigned)n_seg, (unsigned)chunks);
+  const Knobs kb = knobs_of(c->cfg);
+  const uint4* q4 = (const uint4*)d_q;
+  uint32_t* keys = (uint32_t*)c->d_pairkeys.p;
+  unsigned int* state = (unsigned int*)c->d_paircnt.p;
+  if (mode_of(c->cfg) == MODE_POPC)
+    pair_kernel<kRq, MODE_POPC><<<grid, threads, 0, st>>>(q4, nq, train.rows, nt, seg, keys, state, po.train_idx, po.dist, po.good, po.summary, kb);
+  else
+    pair_kernel<kRq, MODE_CSA><<<grid, threads, 0, st>>>(q4, nq, train.rows, nt, seg, keys, state, po.train_idx, po.dist, po.good, po.summary, kb);
+  LC_CUDA(c, cudaGetLastError());
+  c->launches += 1;
+  c->timing.kernel_launches += 1;
+  c->timing.path = 5;
+  return LC_OK;
 }
 
 int stage_query(lc_ctx* c, DevBuf& buf, const uint8_t* q, int64_t n, size_t stride) {
   LC_TRY(ensure(c, buf, (size_t)std::max<int64_t>(n, 1) * LC_DESC_BYTES));
   if (n > 0) LC_TRY(upload_rows(c, (uint8_t*)buf.p, q, n, stride));
+  return LC_OK;
+}
+
+// both sides of a pair match in ONE host-to-device copy: [query rows | train rows] packed in the pinned upload buffer and
+// landed in d_q (the call is latency-bound; a second copy costs as much as the kernel).  Larger pairs take the two-copy road.
+int stage_pair(lc_ctx* c, const uint8_t* q, int64_t nq, size_t qs, const uint8_t* t, int64_t nt, size_t ts, const uint4** d_t) {
+  const size_t q_bytes = ((size_t)nq * LC_DESC_BYTES + 255) & ~size_t(255), t_bytes = (size_t)nt * LC_DESC_BYTES;
+  if (q_bytes + t_bytes > 2 * kPinHalfBytes) {
+    LC_TRY(stage_query(c, c->d_q, q, nq, qs));
+    LC_TRY(stage_query(c, c->d_t, t, nt, ts));
+    *d_t = (const uint4*)c->d_t.p;
+    return LC_OK;
+  }
+  LC_TRY(ensure(c, c->d_q, q_bytes + t_bytes));
+  // earlier asynchronous uploads (lc_loop_check_begin) may still be reading the pinned halves
+  LC_CUDA(c, cudaEventSynchronize(c->pin_ev[0]));
+  LC_CUDA(c, cudaEventSynchronize(c->pin_ev[1]));
+  auto pack = [](uint8_t* dst, const uint8_t* src, int64_t n, size_t stride) {
+    if (stride == LC_DESC_BYTES) {
+      memcpy(dst, src, (size_t)n * LC_DESC_BYTES);
+    } else {
+      for (int64_t r = 0; r < n; ++r) memcpy(dst + (size_t)r * LC_DESC_BYTES, src + (size_t)r * stride, LC_DESC_BYTES);
+    }
+  };
+  pack(c->pin_up, q, nq, qs);
+  pack(c->pin_up + q_bytes, t, nt, ts);
+  LC_CUDA(c, cudaMemcpyAsync(c->d_q.p, c->pin_up, q_bytes + t_bytes, cudaMemcpyHostToDevice, c->stream));
+  // the caller synchronises the stream before it returns, so the pinned buffer is idle again by then
+  *d_t = (const uint4*)((const uint8_t*)c->d_q.p + q_bytes);
   return LC_OK;
 }
 
@@ -622,14 +675,20 @@ void timing_begin(lc_ctx* c) {
   c->timing_on = true;
   cudaEventRecord(c->ev[0], c->stream);
 }
-int timing_end(lc_ctx* c) {
-  LC_CUDA(c, cudaEventRecord(c->ev[3], c->stream));
+// has_d2h = false: the kernels wrote their results straight into mapped pinned memory; ev[2] closes the call
+int timing_end(lc_ctx* c, bool has_d2h = true) {
+  cudaEvent_t last = c->ev[has_d2h ? 3 : 2];
+  if (has_d2h) LC_CUDA(c, cudaEventRecord(c->ev[3], c->stream));
   LC_CUDA(c, cudaStreamSynchronize(c->stream));
   cudaEventElapsedTime(&c->timing.h2d_ms, c->ev[0], c->ev[1]);
   cudaEventElapsedTime(&c->timing.kernel_ms, c->ev[1], c->ev[2]);
-  cudaEventElapsedTime(&c->timing.d2h_ms, c->ev[2], c->ev[3]);
-  cudaEventElapsedTime(&c->timing.total_ms, c->ev[0], c->ev[3]);
+  if (has_d2h) cudaEventElapsedTime(&c->timing.d2h_ms, c->ev[2], c->ev[3]);
+  cudaEventElapsedTime(&c->timing.total_ms, c->ev[0], last);
   c->timing_on = false;
+  if (c->timing.path == 5) {  // the pair kernel is the call's only kernel
+    c->timing.match_ms = c->timing.kernel_ms;
+    c->timing.match_launches = c->timing.kernel_launches;
+  }
   for (size_t i = 0; i + 1 < c->match_ev_used; i += 2) {
     float ms = 0.f;
     if (cudaEventElapsedTime(&ms, c->match_ev[i], c->match_ev[i + 1]) == cudaSuccess) {
@@ -642,18 +701,22 @@ int timing_end(lc_ctx* c) {
 
 int pair_host_impl(lc_ctx* c, int32_t nq, const KfEntry& train, int32_t* train_idx, int32_t* dist, uint8_t* good,
                    int32_t* n_matches, int32_t* min_dist, int32_t* n_good) {
-  // device outputs: idx[nq] dist[nq] summary[2] good[nq]
+  // outputs: idx[nq] dist[nq] summary[2] good[nq].  Up to kPairDirectOutBytes the kernel's finalize step stores them
+  // straight into the pinned result buffer (mapped into the device's address space under unified addressing: posted
+  // writes over PCIe, visible to the host when the stream has drained) - a device-to-host copy would add a stream
+  // operation that costs as much as the kernel.  Larger results go through device memory and one copy.
   const size_t off_dist = (size_t)nq * 4, off_sum = off_dist + (size_t)nq * 4, off_good = off_sum + 8;
   const size_t out_bytes = off_good + (size_t)nq;
-  LC_TRY(ensure(c, c->d_out, out_bytes));
+  const bool direct = out_bytes <= kPairDirectOutBytes;
   LC_TRY(ensure_pin_down(c, out_bytes));
-  uint8_t* d = (uint8_t*)c->d_out.p;
+  if (!direct) LC_TRY(ensure(c, c->d_out, out_bytes));
+  uint8_t* d = direct ? c->pin_down_dev : (uint8_t*)c->d_out.p;
   PairOut po{(int32_t*)d, (int32_t*)(d + off_dist), d + off_good, (int32_t*)(d + off_sum)};
   LC_CUDA(c, cudaEventRecord(c->ev[1], c->stream));
   LC_TRY(pair_device_impl(c, c->stream, c->d_q.p, nq, train, po));
   LC_CUDA(c, cudaEventRecord(c->ev[2], c->stream));
-  LC_CUDA(c, cudaMemcpyAsync(c->pin_down, d, out_bytes, cudaMemcpyDeviceToHost, c->stream));
-  LC_TRY(timing_end(c));
+  if (!direct) LC_CUDA(c, cudaMemcpyAsync(c->pin_down, d, out_bytes, cudaMemcpyDeviceToHost, c->stream));
+  LC_TRY(timing_end(c, !direct));
   const uint8_t* h = c->pin_down;
   if (train_idx) memcpy(train_idx, h, (size_t)nq * 4);
   if (dist) memcpy(dist, h + off_dist, (size_t)nq * 4);
@@ -721,7 +784,7 @@ LC_API void lc_destroy(lc_ctx* c) {
   for (void* p : c->l2s.slabs) cudaFree(p);
   for (DevBuf* b : {&c->l2s.d_kf, &c->d_l2q, &c->d_l2t, &c->d_l2norm, &c->d_l2res, &c->d_l2frames, &c->d_l2out, &c->d_l2img, &c->d_l2tables})
     if (b->p) cudaFree(b->p);
-  for (DevBuf* b : {&c->d_kf, &c->d_q, &c->d_t, &c->d_results, &c->d_best, &c->d_scratch, &c->d_frames, &c->d_pair, &c->d_out, &c->d_counter, &c->d_qimg, &c->d_ablocks})
+  for (DevBuf* b : {&c->d_kf, &c->d_q, &c->d_t, &c->d_results, &c->d_best, &c->d_scratch, &c->d_frames, &c->d_pairkeys, &c->d_paircnt, &c->d_out, &c->d_counter, &c->d_qimg, &c->d_ablocks})
     if (b->p) cudaFree(b->p);
   if (c->pin_up) cudaFreeHost(c->pin_up);
   if (c->pin_down) cudaFreeHost(c->pin_down);
@@ -995,9 +1058,9 @@ LC_API int32_t lc_match_pair(lc_ctx* c, const uint8_t* q, int32_t nq, size_t qs,
   }
   LC_CUDA(c, cudaSetDevice(c->cfg.device));
   timing_begin(c);
-  LC_TRY(stage_query(c, c->d_q, q, nq, qs));
-  LC_TRY(stage_query(c, c->d_t, t, nt, ts));
-  KfEntry train{(const uint4*)c->d_t.p, nt, 0, 0};
+  const uint4* d_t = nullptr;
+  LC_TRY(stage_pair(c, q, nq, qs, t, nt, ts, &d_t));
+  KfEntry train{d_t, nt, 0, 0};
   return pair_host_impl(c, nq, train, train_idx, dist, good, n_matches, min_dist, n_good);
   LC_GUARD_END(c)
 }

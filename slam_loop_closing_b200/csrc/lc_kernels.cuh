@@ -369,6 +369,93 @@ __global__ void __launch_bounds__(256)
   }
 }
 
+// ---------------------------------------------------------------- pair kernel (matchFeatures): one launch
+// The consecutive-frame match is latency-bound (4 M pairs), so the whole of it is ONE launch with every argument passed
+// by value: grid = (row segments, query chunks) folds keys into keys[nq] as the split kernel does and the smallest
+// distance it saw into state[1] (min over queries of min over rows = min over everything, so no second pass is needed);
+// the CTA that finishes last (ticket counter state[0] behind __threadfence) runs the finalize step - 2 x min filter,
+// per-query outputs, summary - in one sweep with its loads issued back to back (each is an L2 round trip), and puts
+// keys[] and state[] back to their idle values (0xffffffff, {0, 0xffffffff}) for the next call: no memset, no table upload.
+constexpr int kPairTailUnroll = 4;
+
+template <int RQ, int MODE>
+__global__ void __launch_bounds__(kMaxThreads, 1)
+    pair_kernel(const uint4* __restrict__ qrows, int nq, const uint4* __restrict__ trows, int nt, int seg_rows,
+                uint32_t* __restrict__ keys, unsigned int* __restrict__ state, int32_t* __restrict__ train_idx,
+                int32_t* __restrict__ dist, uint8_t* __restrict__ good, int32_t* __restrict__ summary, Knobs kb) {
+  __shared__ __align__(128) uint4 tile[kTileRows * 2];
+  __shared__ __align__(8) uint64_t full;
+  __shared__ int red[kMaxThreads / 32];
+  __shared__ unsigned int ticket;
+  const int tid = threadIdx.x, nthr = blockDim.x;
+  const int row0 = blockIdx.x * seg_rows;
+  const int qfirst = blockIdx.y * nthr * RQ;
+  if (row0 < nt && qfirst < nq) {  // (the grid is sized so that this holds; the ticket below is taken either way)
+    const int cnt = min(seg_rows, nt - row0);
+    if (tid == 0) {
+      mbar_init(&full, 1);
+      mbar_fence_init();
+      mbar_expect_tx(&full, cnt * 32);
+      bulk_g2s(tile, trows + (size_t)row0 * 2, cnt * 32, &full);
+    }
+    uint32_t q[RQ][8];
+    load_queries<RQ>(qrows, nq, qfirst + tid, nthr, q);
+    uint32_t best[RQ];
+#pragma unroll
+    for (int s = 0; s < RQ; ++s) best[s] = 0xffffffffu;
+    __syncthreads();  // barrier init visible before anyone waits on it
+    mbar_wait(&full, 0);
+    scan_rows<RQ, MODE>(tile, cnt, (uint32_t)row0, q, best, kb.key_unit);
+    uint32_t lo = 0xffffffffu;
+#pragma unroll
+    for (int s = 0; s < RQ; ++s) {
+      const int i = qfirst + tid + s * nthr;
+      if (i < nq) {
+        atomicMin(keys + i, best[s]);
+        lo = min(lo, best[s]);
+      }
+    }
+    lo = __reduce_min_sync(0xffffffffu, lo);
+    if ((tid & 31) == 0) atomicMin(state + 1, lo >> kKeyShift);
+  }
+  __threadfence();  // this CTA's atomics are ordered before its ticket
+  __syncthreads();
+  if (tid == 0) ticket = atomicAdd(state, 1u);
+  __syncthreads();
+  if (ticket != gridDim.x * gridDim.y - 1) return;
+  __threadfence();  // last CTA: every other CTA's atomics are visible (read past L1)
+  int dmin = (int)__ldcg(state + 1);
+  if (kb.min_init >= 0) dmin = min(dmin, kb.min_init);
+  const int thr = filter_threshold(dmin, kb);
+  int cnt_good = 0;
+  for (int i0 = 0; i0 < nq; i0 += nthr * kPairTailUnroll) {
+    uint32_t key[kPairTailUnroll];
+#pragma unroll
+    for (int u = 0; u < kPairTailUnroll; ++u) {
+      const int i = i0 + u * nthr + tid;
+      key[u] = i < nq ? __ldcg(keys + i) : 0u;
+    }
+#pragma unroll
+    for (int u = 0; u < kPairTailUnroll; ++u) {
+      const int i = i0 + u * nthr + tid;
+      if (i >= nq) continue;
+      keys[i] = 0xffffffffu;
+      const int d = (int)(key[u] >> kKeyShift);
+      const bool g = is_good(d, thr, kb);
+      cnt_good += g ? 1 : 0;
+      if (train_idx) train_idx[i] = (int32_t)(key[u] & kKeyRowMask);
+      if (dist) dist[i] = d;
+      if (good) good[i] = g ? 1 : 0;
+    }
+  }
+  cnt_good = block_sum(cnt_good, red);
+  if (tid == 0) {
+    state[0] = 0u;
+    state[1] = 0xffffffffu;
+    if (summary) { summary[0] = dmin; summary[1] = cnt_good; }
+  }
+}
+
 __global__ void fill_u64_kernel(uint64_t* p, size_t n, uint64_t v) {
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) p[i] = v;
 }

@@ -47,6 +47,26 @@ def _one_case(rng, cases):
             w_res, w_best = c_oracle.loop_check(qs[f], db, [len(k) for k in kfs], fids, curs[f], p, nthreads=16)
             assert np.array_equal(res[f], w_res), (cases, kernel, path, "records")
             assert np.array_equal(best[f], w_best), (cases, kernel, path, "best")
+        # matchFeatures (the single-launch pair kernel): several differently sized pairs through ONE context, so that the
+        # kernel's self-cleaning key buffer and ticket counter are exercised across calls; strided rows now and then
+        pp = Params(filter_floor=int(rng.choice([0, 30])), filter_strict=bool(rng.integers(0, 2)), min_init=int(rng.choice([-1, 100])))
+        with lc.Context(kernel=int(rng.choice([0, 1, 2])), filter_floor=pp.filter_floor, filter_strict=pp.filter_strict, min_init=pp.min_init) as c:
+            for _ in range(4):
+                hi = int(rng.choice([40, 600, 2600, 7000]))
+                a = gen(int(rng.integers(1, hi)), int(rng.integers(1 << 30)))
+                b = gen(int(rng.integers(1, hi)), int(rng.integers(1 << 30)))
+                if rng.integers(0, 3) == 0:  # a planted near-copy: small min_dist, selective filter
+                    b = datagen.noisy_copy(a, int(rng.integers(1 << 30)), p=0.05, n=len(b))
+                if rng.integers(0, 4) == 0:  # non-contiguous rows (a cv::Mat ROI): row stride 48
+                    wide = np.zeros((len(a), 48), np.uint8)
+                    wide[:, :32] = a
+                    a = wide[:, :32]
+                g = c.match_pair(a, b)
+                w = c_oracle.match_features(a, b, pp, nthreads=16)
+                assert c.last_timing().path == 5 and c.last_timing().kernel_launches == 1
+                assert np.array_equal(g["train_idx"], w["train_idx"]) and np.array_equal(g["dist"], w["dist"]) and \
+                    np.array_equal(g["good"].astype(bool), w["good"]) and (g["min_dist"], g["n_good"]) == (w["min_dist"], w["n_good"]), \
+                    (cases, "pair", a.shape, b.shape)
         if cases % 7 == 0:  # the SIFT / L2 path
             a = rng.integers(0, 256, (int(rng.integers(1, 1500)), 128)).astype(np.uint8)
             b = rng.integers(0, 256, (int(rng.integers(1, 1500)), 128)).astype(np.uint8)

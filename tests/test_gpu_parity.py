@@ -48,7 +48,7 @@ def test_pair_c2_uniform_2000x2000(lc, kernel):
     q, t = datagen.uniform(2000, datagen.QUERY_SEED), datagen.uniform(2000, datagen.DB_SEED)
     with _ctx(lc, kernel=kernel) as c:
         _check_pair(c.match_pair(q, t), q, t)
-        assert c.last_timing().path == 2 and c.launch_count() >= 2
+        assert c.last_timing().path == 5 and c.launch_count() == 1  # one launch per pair match
 
 
 @pytest.mark.parametrize("kernel", KERNELS)
