@@ -58,6 +58,13 @@ typedef enum lc_kernel {
                            the winning keyframe afterwards; same result */
 } lc_kernel;
 
+/* CUDA-event timing of host-buffer calls (lc_get_last_timing).  A pair match is a ~50 us call in which each event record
+ * costs ~3 us of stream time, so by default it is not timed (its lc_timing reports path and launches, times read 0). */
+typedef enum lc_timing_mode {
+  LC_TIMING_AUTO = 0, /* every host-buffer call except lc_match_pair / lc_match_vs_keyframe */
+  LC_TIMING_ON = 1    /* every host-buffer call */
+} lc_timing_mode;
+
 /* Parameters of the path.  Defaults (lc_default_config) follow the reference header and README;
  * the extra knobs exist because src/loop_closing.cpp is absent and README prose is ambiguous
  * (SURVEY.md Appendix B). */
@@ -75,7 +82,7 @@ typedef struct lc_config {
   int32_t shard_rank;    /* keyframe k is stored on the context with k % shard_world == shard_rank */
   int32_t shard_world;   /* 1 = unsharded */
   int32_t kernel;        /* lc_kernel */
-  int32_t reserved0;
+  int32_t timing;        /* lc_timing_mode */
   int64_t slab_rows;     /* descriptor rows per device slab; 0 = default (8 Mi rows = 256 MiB) */
 } lc_config;
 

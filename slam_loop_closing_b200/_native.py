@@ -26,7 +26,7 @@ class Config(C.Structure):
                 ("min_loop_gap", C.c_int32), ("min_good", C.c_int32), ("filter_floor", C.c_int32),
                 ("filter_strict", C.c_int32), ("min_init", C.c_int32), ("gap_strict", C.c_int32),
                 ("thr_inclusive", C.c_int32), ("shard_rank", C.c_int32), ("shard_world", C.c_int32),
-                ("kernel", C.c_int32), ("reserved0", C.c_int32), ("slab_rows", C.c_int64)]
+                ("kernel", C.c_int32), ("timing", C.c_int32), ("slab_rows", C.c_int64)]
 
 
 L2_RESULT = np.dtype([("frame_id", "<i4"), ("n_kf", "<i4"), ("n_good", "<i4"), ("reserved", "<i4")])  # lc_l2_result

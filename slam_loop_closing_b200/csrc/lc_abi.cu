@@ -196,6 +196,7 @@ int validate(lc_ctx* c, const lc_config& g) {
     return fail(c, LC_ERR_INVALID, "shard_rank %d / shard_world %d invalid", g.shard_rank, g.shard_world);
   if (g.kernel < LC_KERNEL_AUTO || g.kernel > LC_KERNEL_MXF4) return fail(c, LC_ERR_INVALID, "unknown kernel %d", g.kernel);
   if (g.slab_rows < 0) return fail(c, LC_ERR_INVALID, "slab_rows < 0");
+  if (g.timing != LC_TIMING_AUTO && g.timing != LC_TIMING_ON) return fail(c, LC_ERR_INVALID, "timing = %d is not an lc_timing_mode", g.timing);
   if (g.min_loop_gap < -(1 << 30) || g.min_loop_gap > (1 << 30)) return fail(c, LC_ERR_INVALID, "min_loop_gap out of range");
   return LC_OK;
 }
@@ -669,14 +670,21 @@ int stage_pair(lc_ctx* c, const uint8_t* q, int64_t nq, size_t qs, const uint8_t
   return LC_OK;
 }
 
-void timing_begin(lc_ctx* c) {
+// events = false: the call's path and launch count are still reported, its times read 0
+void timing_begin(lc_ctx* c, bool events = true) {
   c->timing = lc_timing{};
   c->match_ev_used = 0;
-  c->timing_on = true;
-  cudaEventRecord(c->ev[0], c->stream);
+  c->timing_on = events;
+  if (events) cudaEventRecord(c->ev[0], c->stream);
 }
+// a pair match is a ~50 us call in which every event record costs ~3 us of stream time: timed only on request
+bool pair_events(const lc_ctx* c) { return c->cfg.timing == LC_TIMING_ON; }
 // has_d2h = false: the kernels wrote their results straight into mapped pinned memory; ev[2] closes the call
 int timing_end(lc_ctx* c, bool has_d2h = true) {
+  if (!c->timing_on) {
+    LC_CUDA(c, cudaStreamSynchronize(c->stream));
+    return LC_OK;
+  }
   cudaEvent_t last = c->ev[has_d2h ? 3 : 2];
   if (has_d2h) LC_CUDA(c, cudaEventRecord(c->ev[3], c->stream));
   LC_CUDA(c, cudaStreamSynchronize(c->stream));
@@ -712,9 +720,9 @@ int pair_host_impl(lc_ctx* c, int32_t nq, const KfEntry& train, int32_t* train_i
   if (!direct) LC_TRY(ensure(c, c->d_out, out_bytes));
   uint8_t* d = direct ? c->pin_down_dev : (uint8_t*)c->d_out.p;
   PairOut po{(int32_t*)d, (int32_t*)(d + off_dist), d + off_good, (int32_t*)(d + off_sum)};
-  LC_CUDA(c, cudaEventRecord(c->ev[1], c->stream));
+  if (c->timing_on) LC_CUDA(c, cudaEventRecord(c->ev[1], c->stream));
   LC_TRY(pair_device_impl(c, c->stream, c->d_q.p, nq, train, po));
-  LC_CUDA(c, cudaEventRecord(c->ev[2], c->stream));
+  if (c->timing_on) LC_CUDA(c, cudaEventRecord(c->ev[2], c->stream));
   if (!direct) LC_CUDA(c, cudaMemcpyAsync(c->pin_down, d, out_bytes, cudaMemcpyDeviceToHost, c->stream));
   LC_TRY(timing_end(c, !direct));
   const uint8_t* h = c->pin_down;
@@ -771,6 +779,7 @@ LC_API void lc_default_config(lc_config* g) {
   g->shard_rank = 0;
   g->shard_world = 1;
   g->kernel = LC_KERNEL_AUTO;
+  g->timing = LC_TIMING_AUTO;
   g->slab_rows = 0;
 }
 
@@ -1057,7 +1066,7 @@ LC_API int32_t lc_match_pair(lc_ctx* c, const uint8_t* q, int32_t nq, size_t qs,
     return LC_OK;
   }
   LC_CUDA(c, cudaSetDevice(c->cfg.device));
-  timing_begin(c);
+  timing_begin(c, pair_events(c));
   const uint4* d_t = nullptr;
   LC_TRY(stage_pair(c, q, nq, qs, t, nt, ts, &d_t));
   KfEntry train{d_t, nt, 0, 0};
@@ -1078,7 +1087,7 @@ LC_API int32_t lc_match_vs_keyframe(lc_ctx* c, const uint8_t* q, int32_t nq, siz
     return LC_OK;
   }
   LC_CUDA(c, cudaSetDevice(c->cfg.device));
-  timing_begin(c);
+  timing_begin(c, pair_events(c));
   LC_TRY(stage_query(c, c->d_q, q, nq, qs));
   return pair_host_impl(c, nq, train, train_idx, dist, good, n_matches, min_dist, n_good);
   LC_GUARD_END(c)

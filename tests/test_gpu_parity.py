@@ -51,6 +51,22 @@ def test_pair_c2_uniform_2000x2000(lc, kernel):
         assert c.last_timing().path == 5 and c.launch_count() == 1  # one launch per pair match
 
 
+def test_pair_timing_modes(lc):
+    """lc_config.timing: pair matches are event-timed only on request (LC_TIMING_ON); path and launches always report."""
+    q, t = datagen.uniform(700, 1), datagen.uniform(900, 2)
+    with lc.Context() as c:
+        _check_pair(c.match_pair(q, t), q, t)
+        tm = c.last_timing()
+        assert (tm.path, tm.kernel_launches) == (5, 1) and tm.kernel_ms == 0.0 and tm.total_ms == 0.0
+    with lc.Context(timing=1) as c:
+        _check_pair(c.match_pair(q, t), q, t)
+        tm = c.last_timing()
+        assert (tm.path, tm.kernel_launches) == (5, 1) and tm.kernel_ms > 0.0 and tm.total_ms >= tm.kernel_ms
+        assert tm.match_ms == tm.kernel_ms and tm.d2h_ms == 0.0  # results are stored straight into pinned host memory
+    with pytest.raises(lc.LcError):
+        lc.Context(timing=7)
+
+
 @pytest.mark.parametrize("kernel", KERNELS)
 @pytest.mark.parametrize("nq,nt", [(1, 1), (1, 700), (700, 1), (31, 33), (32, 32), (33, 31), (255, 257), (300, 700),
                                    (1999, 2000), (2000, 1999), (2081, 2081), (5000, 300), (300, 5000), (4097, 513)])

@@ -1,6 +1,6 @@
 /* Latency of lc_match_pair through the C ABI from a plain C caller (no Python in the loop): BASELINE config 2.
  * gcc -O2 -I include tools/pair_latency.c slam_loop_closing_b200/csrc/liblc_b200.so -Wl,-rpath,$PWD/slam_loop_closing_b200/csrc -o build/pair_latency
- * usage: pair_latency [nq] [nt] [iters] */
+ * usage: pair_latency [nq] [nt] [iters] [timing: 0 = default (pair calls not event-timed), 1 = timed] */
 #define _POSIX_C_SOURCE 199309L
 #include <stdio.h>
 #include <stdlib.h>
@@ -15,7 +15,7 @@ static double now_us(void) {
 static int cmp(const void* a, const void* b) { return (*(const double*)a > *(const double*)b) - (*(const double*)a < *(const double*)b); }
 
 int main(int argc, char** argv) {
-  const int nq = argc > 1 ? atoi(argv[1]) : 2000, nt = argc > 2 ? atoi(argv[2]) : 2000, iters = argc > 3 ? atoi(argv[3]) : 500;
+  const int nq = argc > 1 ? atoi(argv[1]) : 2000, nt = argc > 2 ? atoi(argv[2]) : 2000, iters = argc > 3 ? atoi(argv[3]) : 500, timing = argc > 4 ? atoi(argv[4]) : 0;
   uint8_t* q = malloc((size_t)nq * 32);
   uint8_t* t = malloc((size_t)nt * 32);
   unsigned s = 12345u;
@@ -26,7 +26,10 @@ int main(int argc, char** argv) {
   uint8_t* good = malloc((size_t)nq);
   double* us = malloc(sizeof(double) * (size_t)iters);
   lc_ctx* c = NULL;
-  if (lc_create(NULL, &c) != 0) { fprintf(stderr, "lc_create: %s\n", lc_last_error(NULL)); return 1; }
+  lc_config cfg;
+  lc_default_config(&cfg);
+  cfg.timing = timing;
+  if (lc_create(&cfg, &c) != 0) { fprintf(stderr, "lc_create: %s\n", lc_last_error(NULL)); return 1; }
   int32_t nm, md, ng;
   double h2d = 0, ker = 0, d2h = 0, mk = 0;
   lc_timing tm;

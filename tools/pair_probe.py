@@ -12,7 +12,8 @@ kernel = int(sys.argv[3]) if len(sys.argv) > 3 else 0
 rng = np.random.default_rng(1)
 q = rng.integers(0, 256, (nq, 32), dtype=np.uint8)
 t = rng.integers(0, 256, (nt, 32), dtype=np.uint8)
-with lc.Context(kernel=kernel) as c:
+timing = int(sys.argv[4]) if len(sys.argv) > 4 else 0  # 1: event-time the pair call (costs ~10 us of the call)
+with lc.Context(kernel=kernel, timing=timing) as c:
     for _ in range(20):
         c.match_pair(q, t)
     e2e, h2d, ker, d2h, mk = [], [], [], [], []
