@@ -38,6 +38,8 @@ constexpr int64_t kDefaultSlabRows = 8ll << 20;
 constexpr size_t kScratchBudgetBytes = 256u << 20;
 constexpr int kFusedMaxNq = kMaxThreads * 8;
 constexpr size_t kPairDirectOutBytes = 256u << 10;  // pair results up to this size are stored straight into pinned host memory
+constexpr long long kTensorMinPairs = 30ll << 20;  // loop checks of fewer pairs AND fewer (query block, keyframe) units than SMs stay on the integer kernels
+constexpr double kTimedMinPairs = 1e9;  // LC_TIMING_AUTO: loop checks of fewer pairs are not event-timed
 constexpr int kPairMinSegRows = 8;  // fewest train rows a pair-kernel CTA scans
 
 struct Shape {  // launch shape for nq queries
@@ -72,7 +74,7 @@ struct lc_ctx {
   uint8_t* pin_down = nullptr;
   uint8_t* pin_down_dev = nullptr;  // the same buffer as the device addresses it (results stored by kernels directly)
   size_t pin_down_cap = 0;
-  DevBuf d_q, d_t, d_results, d_best, d_scratch, d_frames, d_pairkeys, d_paircnt, d_out, d_counter, d_qimg, d_ablocks;
+  DevBuf d_q, d_t, d_results, d_scratch, d_frames, d_pairkeys, d_paircnt, d_out, d_counter, d_qimg, d_ablocks;
 
   lc_timing timing{};
   int64_t launches = 0;
@@ -336,12 +338,23 @@ struct PairOut {  // optional per-query outputs of the pair API (device pointers
   int32_t* summary = nullptr;
 };
 
+int fill_best(lc_ctx* c, cudaStream_t st, uint64_t* d_best, size_t n) {
+  if (!d_best || n == 0) return LC_OK;
+  const int blocks = (int)std::min<size_t>((n + 255) / 256, 1024);
+  fill_u64_kernel<<<blocks, 256, 0, st>>>(d_best, n, ~0ull);
+  LC_CUDA(c, cudaGetLastError());
+  c->launches += 1;
+  c->timing.kernel_launches += 1;
+  return LC_OK;
+}
+
 // Match n_frames query frames against n_kf keyframes (device tables) on `st`.
 // h_frames mirrors d_frames (needed for nq).  max_rows = max n over the keyframes.
 int run_match(lc_ctx* c, cudaStream_t st, const KfEntry* d_kfs, int n_kf, int max_rows, const QFrame* d_frames,
-              const QFrame* h_frames, int n_frames, lc_kf_result* d_results, Knobs kb, bool full_tiles) {
+              const QFrame* h_frames, int n_frames, lc_kf_result* d_results, Knobs kb, bool full_tiles, uint64_t* d_best, size_t best_n) {
+  // d_best[best_n]: the frames' per-query global bests, to be put to all ones before the first kernel folds into them
   const long long n_items = (long long)n_kf * n_frames;
-  if (n_items == 0) return LC_OK;
+  if (n_items == 0) return fill_best(c, st, d_best, best_n);
   if (n_items > 0x7fffffffll) return fail(c, LC_ERR_INVALID, "too many (frame, keyframe) items: %lld", n_items);
   int max_nq = 0;
   for (int f = 0; f < n_frames; ++f) max_nq = std::max(max_nq, h_frames[f].nq);
@@ -365,7 +378,9 @@ int run_match(lc_ctx* c, cudaStream_t st, const KfEntry* d_kfs, int n_kf, int ma
         total_tiles += tiles.back();
       }
     const int n_ab = (int)blocks.size();
-    if ((long long)n_ab * n_kf >= c->num_sms) {
+    // Worth it from ~8 full keyframes on (measured, tools/loop_latency.py: at 67 keyframes x 2000 rows the tensor path takes
+    // a third of the integer kernels' end-to-end time although its CTAs - one per (query block, keyframe) - fill half the SMs).
+    if ((long long)n_ab * n_kf >= c->num_sms || (long long)total_tiles * tc::kQTile * n_kf * max_rows >= kTensorMinPairs) {
       // scratch: one distance (mxf4: u16) or key (int8: u32) per (frame, keyframe, query); rows start 16-byte aligned.
       // The keyframes go through in batches of kc_max bounded by the scratch budget.
       const int stride = (max_nq + 7) & ~7;
@@ -429,10 +444,13 @@ int run_match(lc_ctx* c, cudaStream_t st, const KfEntry* d_kfs, int n_kf, int ma
           c->tables_host.swap(img);
         }
       }
-      if (want_fp4)
-        fx::expand_queries_fp4_kernel<<<n_ab, 512, 0, st>>>((const fx::ABlock*)d_blocks, d_frames, (uint8_t*)c->d_qimg.p);
-      else
+      if (want_fp4) {
+        fx::expand_queries_fp4_kernel<<<dim3(n_ab, fx::kQTilesPerCta), fx::kExpandThreads, 0, st>>>((const fx::ABlock*)d_blocks, d_frames,
+                                                                                                  (uint8_t*)c->d_qimg.p, d_best != nullptr);
+      } else {
+        LC_TRY(fill_best(c, st, d_best, best_n));
         tc::expand_queries_kernel<<<n_ab, 256, 0, st>>>(d_blocks, d_frames, (uint8_t*)c->d_qimg.p);
+      }
       LC_CUDA(c, cudaGetLastError());
       if (!c->smem_attr_set) {  // per device, so per context
         LC_CUDA(c, cudaFuncSetAttribute(tc::tensor_match_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kSmemAlloc));
@@ -495,6 +513,7 @@ int run_match(lc_ctx* c, cudaStream_t st, const KfEntry* d_kfs, int n_kf, int ma
     }
   }
 
+  LC_TRY(fill_best(c, st, d_best, best_n));
   // ---- whole-keyframe scan: enough items to fill every CTA slot many times over
   if (max_nq <= kFusedMaxNq && max_nq > 0) {
     const Shape sh = scan_shape(max_nq);
@@ -561,37 +580,40 @@ int run_match(lc_ctx* c, cudaStream_t st, const KfEntry* d_kfs, int n_kf, int ma
   return LC_OK;
 }
 
-int fill_best(lc_ctx* c, cudaStream_t st, uint64_t* d_best, size_t n) {
-  if (!d_best || n == 0) return LC_OK;
-  const int blocks = (int)std::min<size_t>((n + 255) / 256, 1024);
-  fill_u64_kernel<<<blocks, 256, 0, st>>>(d_best, n, ~0ull);
-  LC_CUDA(c, cudaGetLastError());
-  c->launches += 1;
-  c->timing.kernel_launches += 1;
-  return LC_OK;
-}
-
-// loop check of n_frames device-resident frames (rows concatenated at d_q) against the local store
-int loop_check_device_impl(lc_ctx* c, cudaStream_t st, int n_frames, const void* d_q, const int32_t* nq,
-                           const int32_t* cur_ids, lc_kf_result* d_results, uint64_t* d_best) {
-  if (n_frames <= 0) return LC_OK;
+// the frame table of a loop check whose rows lie concatenated at d_q
+int build_frames(lc_ctx* c, int n_frames, const void* d_q, const int32_t* nq, const int32_t* cur_ids, uint64_t* d_best,
+                 std::vector<QFrame>& hf, size_t* rows) {
   if ((uintptr_t)d_q % 16 != 0) return fail(c, LC_ERR_INVALID, "d_q must be 16-byte aligned");
-  LC_TRY(sync_kf_table(c));
-  std::vector<QFrame> hf((size_t)n_frames);
+  hf.resize((size_t)n_frames);
   size_t row = 0;
   for (int f = 0; f < n_frames; ++f) {
     if (nq[f] < 0 || nq[f] > LC_MAX_ROWS_PER_KF) return fail(c, LC_ERR_INVALID, "nq[%d] = %d out of range", f, nq[f]);
     hf[f] = QFrame{(const uint4*)d_q + 2 * row, nq[f], cur_ids[f], d_best ? d_best + row : nullptr};
     row += (size_t)nq[f];
   }
-  LC_TRY(fill_best(c, st, d_best, row));
-  const int n_kf = (int)c->h_kf.size();
-  if (n_kf == 0) return LC_OK;
+  *rows = row;
+  return LC_OK;
+}
+
+// loop check of the frames in hf (device copy of the table at d_frames) against the local store
+int loop_check_run(lc_ctx* c, cudaStream_t st, const std::vector<QFrame>& hf, const QFrame* d_frames, size_t rows,
+                   lc_kf_result* d_results, uint64_t* d_best) {
+  LC_TRY(sync_kf_table(c));
+  return run_match(c, st, (const KfEntry*)c->d_kf.p, (int)c->h_kf.size(), c->max_n_local, d_frames, hf.data(), (int)hf.size(), d_results,
+                   knobs_of(c->cfg), c->n_partial_kf == 0, d_best, rows);
+}
+
+// loop check of n_frames device-resident frames (rows concatenated at d_q) against the local store
+int loop_check_device_impl(lc_ctx* c, cudaStream_t st, int n_frames, const void* d_q, const int32_t* nq,
+                           const int32_t* cur_ids, lc_kf_result* d_results, uint64_t* d_best) {
+  if (n_frames <= 0) return LC_OK;
+  std::vector<QFrame> hf;
+  size_t rows = 0;
+  LC_TRY(build_frames(c, n_frames, d_q, nq, cur_ids, d_best, hf, &rows));
   LC_TRY(ensure(c, c->d_frames, hf.size() * sizeof(QFrame)));
   // pageable source: the runtime stages it before returning, so `hf` may die with this frame
   LC_CUDA(c, cudaMemcpyAsync(c->d_frames.p, hf.data(), hf.size() * sizeof(QFrame), cudaMemcpyHostToDevice, st));
-  return run_match(c, st, (const KfEntry*)c->d_kf.p, n_kf, c->max_n_local, (const QFrame*)c->d_frames.p, hf.data(), n_frames,
-                   d_results, knobs_of(c->cfg), c->n_partial_kf == 0);
+  return loop_check_run(c, st, hf, (const QFrame*)c->d_frames.p, rows, d_results, d_best);
 }
 
 // matchFeatures on device-resident rows: one launch of pair_kernel (lc_kernels.cuh); nq, nt > 0
@@ -679,14 +701,19 @@ void timing_begin(lc_ctx* c, bool events = true) {
 }
 // a pair match is a ~50 us call in which every event record costs ~3 us of stream time: timed only on request
 bool pair_events(const lc_ctx* c) { return c->cfg.timing == LC_TIMING_ON; }
+// a loop check is timed by default once it is large enough for six event records (~20 us) not to matter
+bool loop_events(const lc_ctx* c, int64_t query_rows) {
+  return c->cfg.timing == LC_TIMING_ON || (double)query_rows * (double)c->l_rows >= kTimedMinPairs;
+}
 // has_d2h = false: the kernels wrote their results straight into mapped pinned memory; ev[2] closes the call
-int timing_end(lc_ctx* c, bool has_d2h = true) {
+// record_last = false: ev[3] was recorded when the work was queued (lc_loop_check_begin), not now
+int timing_end(lc_ctx* c, bool has_d2h = true, bool record_last = true) {
   if (!c->timing_on) {
     LC_CUDA(c, cudaStreamSynchronize(c->stream));
     return LC_OK;
   }
   cudaEvent_t last = c->ev[has_d2h ? 3 : 2];
-  if (has_d2h) LC_CUDA(c, cudaEventRecord(c->ev[3], c->stream));
+  if (has_d2h && record_last) LC_CUDA(c, cudaEventRecord(c->ev[3], c->stream));
   LC_CUDA(c, cudaStreamSynchronize(c->stream));
   cudaEventElapsedTime(&c->timing.h2d_ms, c->ev[0], c->ev[1]);
   cudaEventElapsedTime(&c->timing.kernel_ms, c->ev[1], c->ev[2]);
@@ -793,7 +820,7 @@ LC_API void lc_destroy(lc_ctx* c) {
   for (void* p : c->l2s.slabs) cudaFree(p);
   for (DevBuf* b : {&c->l2s.d_kf, &c->d_l2q, &c->d_l2t, &c->d_l2norm, &c->d_l2res, &c->d_l2frames, &c->d_l2out, &c->d_l2img, &c->d_l2tables})
     if (b->p) cudaFree(b->p);
-  for (DevBuf* b : {&c->d_kf, &c->d_q, &c->d_t, &c->d_results, &c->d_best, &c->d_scratch, &c->d_frames, &c->d_pairkeys, &c->d_paircnt, &c->d_out, &c->d_counter, &c->d_qimg, &c->d_ablocks})
+  for (DevBuf* b : {&c->d_kf, &c->d_q, &c->d_t, &c->d_results, &c->d_scratch, &c->d_frames, &c->d_pairkeys, &c->d_paircnt, &c->d_out, &c->d_counter, &c->d_qimg, &c->d_ablocks})
     if (b->p) cudaFree(b->p);
   if (c->pin_up) cudaFreeHost(c->pin_up);
   if (c->pin_down) cudaFreeHost(c->pin_down);
@@ -1207,24 +1234,45 @@ int loop_check_enqueue_impl(lc_ctx* c, int32_t n_frames, const uint8_t* const* q
   c->pending.rows = rows;
   if (n_frames == 0) return LC_OK;
   LC_CUDA(c, cudaSetDevice(c->cfg.device));
-  timing_begin(c);
-  LC_TRY(ensure(c, c->d_q, (size_t)std::max<int64_t>(rows, 1) * LC_DESC_BYTES));
-  int64_t r0 = 0;
-  for (int f = 0; f < n_frames; ++f) {
-    if (nq[f] > 0) LC_TRY(upload_rows(c, (uint8_t*)c->d_q.p + (size_t)r0 * LC_DESC_BYTES, q[f], nq[f], LC_DESC_BYTES));
-    r0 += nq[f];
-  }
+  timing_begin(c, loop_events(c, rows));
+  // device side: [query rows | frame table] in d_q, [per-keyframe records | per-query bests] in d_results - one copy in
+  // and one copy out when the rows fit the pinned upload buffer (a small check is a chain of latencies, not bandwidth)
+  const size_t row_bytes = ((size_t)rows * LC_DESC_BYTES + 255) & ~size_t(255), table_bytes = (size_t)n_frames * sizeof(QFrame);
   const size_t res_bytes = (size_t)c->pending.n_res * sizeof(lc_kf_result), best_bytes = want_best ? (size_t)rows * 8 : 0;
-  LC_TRY(ensure(c, c->d_results, std::max<size_t>(res_bytes, 16)));
-  LC_TRY(ensure(c, c->d_best, std::max<size_t>(best_bytes, 16)));
+  LC_TRY(ensure(c, c->d_q, row_bytes + table_bytes));
+  LC_TRY(ensure(c, c->d_results, std::max<size_t>(res_bytes + best_bytes, 16)));
   LC_TRY(ensure_pin_down(c, res_bytes + best_bytes + 16));
-  LC_CUDA(c, cudaEventRecord(c->ev[1], c->stream));
-  LC_TRY(loop_check_device_impl(c, c->stream, n_frames, c->d_q.p, nq, cur_ids, (lc_kf_result*)c->d_results.p,
-                                want_best ? (uint64_t*)c->d_best.p : nullptr));
-  LC_CUDA(c, cudaEventRecord(c->ev[2], c->stream));
-  if (res_bytes) LC_CUDA(c, cudaMemcpyAsync(c->pin_down, c->d_results.p, res_bytes, cudaMemcpyDeviceToHost, c->stream));
-  if (best_bytes) LC_CUDA(c, cudaMemcpyAsync(c->pin_down + res_bytes, c->d_best.p, best_bytes, cudaMemcpyDeviceToHost, c->stream));
-  LC_CUDA(c, cudaEventRecord(c->ev[3], c->stream));
+  lc_kf_result* d_results = (lc_kf_result*)c->d_results.p;
+  uint64_t* d_best = want_best ? (uint64_t*)((uint8_t*)c->d_results.p + res_bytes) : nullptr;  // res_bytes is a multiple of 16
+  std::vector<QFrame> hf;
+  size_t rows_built = 0;
+  LC_TRY(build_frames(c, n_frames, c->d_q.p, nq, cur_ids, d_best, hf, &rows_built));
+  const QFrame* d_frames = (const QFrame*)((const uint8_t*)c->d_q.p + row_bytes);
+  if (row_bytes + table_bytes <= 2 * kPinHalfBytes) {
+    LC_CUDA(c, cudaEventSynchronize(c->pin_ev[0]));  // earlier uploads have drained both pinned halves
+    LC_CUDA(c, cudaEventSynchronize(c->pin_ev[1]));
+    size_t off = 0;
+    for (int f = 0; f < n_frames; ++f) {
+      memcpy(c->pin_up + off, q[f], (size_t)nq[f] * LC_DESC_BYTES);
+      off += (size_t)nq[f] * LC_DESC_BYTES;
+    }
+    memcpy(c->pin_up + row_bytes, hf.data(), table_bytes);
+    LC_CUDA(c, cudaMemcpyAsync(c->d_q.p, c->pin_up, row_bytes + table_bytes, cudaMemcpyHostToDevice, c->stream));
+    LC_CUDA(c, cudaEventRecord(c->pin_ev[0], c->stream));  // lc_loop_check_begin returns with the copy in flight
+    LC_CUDA(c, cudaEventRecord(c->pin_ev[1], c->stream));
+  } else {
+    int64_t r0 = 0;
+    for (int f = 0; f < n_frames; ++f) {
+      if (nq[f] > 0) LC_TRY(upload_rows(c, (uint8_t*)c->d_q.p + (size_t)r0 * LC_DESC_BYTES, q[f], nq[f], LC_DESC_BYTES));
+      r0 += nq[f];
+    }
+    LC_CUDA(c, cudaMemcpyAsync((void*)d_frames, hf.data(), table_bytes, cudaMemcpyHostToDevice, c->stream));  // pageable: staged before the call returns
+  }
+  if (c->timing_on) LC_CUDA(c, cudaEventRecord(c->ev[1], c->stream));
+  LC_TRY(loop_check_run(c, c->stream, hf, d_frames, rows_built, d_results, d_best));
+  if (c->timing_on) LC_CUDA(c, cudaEventRecord(c->ev[2], c->stream));
+  if (res_bytes + best_bytes) LC_CUDA(c, cudaMemcpyAsync(c->pin_down, c->d_results.p, res_bytes + best_bytes, cudaMemcpyDeviceToHost, c->stream));
+  if (c->timing_on) LC_CUDA(c, cudaEventRecord(c->ev[3], c->stream));
   c->pending.res_bytes = res_bytes;
   c->pending.best_bytes = best_bytes;
   c->pending.queued = true;
@@ -1245,7 +1293,7 @@ int loop_check_collect(lc_ctx* c, lc_kf_result* results, int64_t results_cap, ui
   c->pending.active = false;
   if (p.queued) {
     LC_CUDA(c, cudaSetDevice(c->cfg.device));
-    LC_TRY(timing_end(c));
+    LC_TRY(timing_end(c, true, false));
   }
   if (p.n_res > 0 && (!results || results_cap < p.n_res))
     return fail(c, LC_ERR_CAPACITY, "results_cap %lld < %lld", (long long)results_cap, (long long)p.n_res);

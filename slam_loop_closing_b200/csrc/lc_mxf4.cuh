@@ -90,15 +90,24 @@ __device__ __forceinline__ uint4 expand_word_fp4(uint32_t x) {
 // 16-byte chunk index XOR (row & 7)  (Swizzle<3,4,3>)
 __device__ __forceinline__ uint32_t tile_offset(int r, int w) { return (uint32_t)r * 128u + (((uint32_t)w ^ ((uint32_t)r & 7u)) << 4); }
 
-// one launch per loop check: every (frame, 1024-query block) gets its A image in global memory
-__global__ void expand_queries_fp4_kernel(const ABlock* __restrict__ blocks, const QFrame* __restrict__ frames, uint8_t* img_base) {
+// one launch per loop check, grid (query blocks, 8): every 128-query tile of every (frame, 1024-query block) gets its A
+// image in global memory.  fill_best: the per-query global best of those queries is also put to its idle value here
+// (all ones), which saves the loop check a launch of its own for that.
+constexpr int kExpandThreads = 512;
+__global__ void __launch_bounds__(kExpandThreads)
+    expand_queries_fp4_kernel(const ABlock* __restrict__ blocks, const QFrame* __restrict__ frames, uint8_t* img_base, int fill_best) {
   const ABlock ab = blocks[blockIdx.x];
   const QFrame fr = frames[ab.frame];
-  uint8_t* img = img_base + (size_t)blockIdx.x * kABytes;
-  for (int idx = threadIdx.x; idx < kQPerCta * 8; idx += blockDim.x) {
-    const int ql = idx >> 3, w = idx & 7, q = ab.q0 + ql;
+  const int tile = blockIdx.y;
+  uint8_t* img = img_base + (size_t)blockIdx.x * kABytes + (size_t)tile * kATileBytes;
+  for (int idx = threadIdx.x; idx < kQTile * 8; idx += kExpandThreads) {
+    const int r = idx >> 3, w = idx & 7, q = ab.q0 + tile * kQTile + r;
     const uint32_t bits = q < fr.nq ? __ldg(reinterpret_cast<const uint32_t*>(fr.q) + (size_t)q * 8 + w) : 0u;
-    *reinterpret_cast<uint4*>(img + (size_t)(ql / kQTile) * kATileBytes + tile_offset(ql & (kQTile - 1), w)) = expand_word_fp4(bits);
+    *reinterpret_cast<uint4*>(img + tile_offset(r, w)) = expand_word_fp4(bits);
+  }
+  if (fill_best && fr.best_packed && threadIdx.x < kQTile) {
+    const int q = ab.q0 + tile * kQTile + threadIdx.x;
+    if (q < fr.nq) fr.best_packed[q] = ~0ull;
   }
 }
 
