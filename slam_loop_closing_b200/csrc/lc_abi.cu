@@ -461,6 +461,16 @@ int run_match(lc_ctx* c, cudaStream_t st, const KfEntry* d_kfs, int n_kf, int ma
       LC_TRY(ensure(c, c->d_scratch, (size_t)kc_max * n_frames * stride * elem));
       c->launches += 1;
       c->timing.kernel_launches += 1;
+      bool any_best = false;
+      long long total_nq = 0;
+      for (int f = 0; f < n_frames; ++f) {
+        any_best = any_best || h_frames[f].best_packed != nullptr;
+        total_nq += h_frames[f].nq;
+      }
+      // winning keyframe of each query -> winning row (OpenCV's lowest-index order): its own launch after the last batch,
+      // or fused with the finalize step when there is a single batch
+      const int resolve_grid = (int)std::max<long long>(1, std::min<long long>((total_nq + 7) / 8, 4ll * c->num_sms));
+      const bool fused_finish = want_fp4 && any_best && kc_max >= n_kf;
       for (int k0 = 0; k0 < n_kf; k0 += (int)kc_max) {
         const int kc = (int)std::min<long long>(kc_max, n_kf - k0);
         if (want_fp4) {
@@ -476,8 +486,13 @@ int run_match(lc_ctx* c, cudaStream_t st, const KfEntry* d_kfs, int n_kf, int ma
             else launch(fx::mxf4_match_kernel<false>);
           }
           LC_CUDA(c, cudaGetLastError());
-          fx::finalize_dist_kernel<<<(kc * n_frames + fx::kFinWarps - 1) / fx::kFinWarps, fx::kFinWarps * 32, 0, st>>>(
-              d_kfs, n_kf, k0, kc, d_frames, n_frames, (const uint16_t*)c->d_scratch.p, stride, d_results, kb);
+          const int n_fin = (kc * n_frames + fx::kFinWarps - 1) / fx::kFinWarps;
+          if (fused_finish)
+            fx::finish_kernel<<<n_fin + resolve_grid, 256, 0, st>>>(n_fin, d_kfs, n_kf, d_frames, n_frames, (const uint16_t*)c->d_scratch.p, stride,
+                                                                     d_results, kb);
+          else
+            fx::finalize_dist_kernel<<<n_fin, fx::kFinWarps * 32, 0, st>>>(d_kfs, n_kf, k0, kc, d_frames, n_frames,
+                                                                           (const uint16_t*)c->d_scratch.p, stride, d_results, kb);
         } else {
           LC_CUDA(c, cudaMemsetAsync(c->d_scratch.p, 0xff, (size_t)kc * n_frames * stride * 4, st));
           {
@@ -493,20 +508,11 @@ int run_match(lc_ctx* c, cudaStream_t st, const KfEntry* d_kfs, int n_kf, int ma
         c->launches += 2;
         c->timing.kernel_launches += 2;
       }
-      if (want_fp4) {
-        bool any_best = false;
-        long long total_nq = 0;
-        for (int f = 0; f < n_frames; ++f) {
-          any_best = any_best || h_frames[f].best_packed != nullptr;
-          total_nq += h_frames[f].nq;
-        }
-        if (any_best) {  // winning keyframe of each query -> winning row (OpenCV's lowest-index order)
-          const int grid = (int)std::min<long long>((total_nq + 7) / 8, 4ll * c->num_sms);
-          fx::resolve_best_kernel<<<std::max(grid, 1), 256, 0, st>>>(d_kfs, d_frames, n_frames);
-          LC_CUDA(c, cudaGetLastError());
-          c->launches += 1;
-          c->timing.kernel_launches += 1;
-        }
+      if (want_fp4 && any_best && !fused_finish) {
+        fx::resolve_best_kernel<<<resolve_grid, 256, 0, st>>>(d_kfs, d_frames, n_frames);
+        LC_CUDA(c, cudaGetLastError());
+        c->launches += 1;
+        c->timing.kernel_launches += 1;
       }
       c->timing.path = want_fp4 ? 4 : 3;
       return LC_OK;

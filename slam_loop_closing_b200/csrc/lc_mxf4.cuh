@@ -452,11 +452,11 @@ __global__ void __launch_bounds__(kThreads, 1)
 // The 16-bit distances of one match (<= 4 KiB) are read once with 128-bit loads and stay in registers for both passes.
 constexpr int kFinWarps = 8;
 constexpr int kFinMaxVec = 16;  // 16 x 32 lanes x 8 distances = 4096 queries per pass
-__global__ void __launch_bounds__(kFinWarps * 32)
-    finalize_dist_kernel(const KfEntry* __restrict__ kfs, int n_kf, int k0, int kc, const QFrame* __restrict__ frames, int n_frames,
-                         const uint16_t* __restrict__ scratch, int scratch_stride, lc_kf_result* __restrict__ results, Knobs kb) {
+__device__ __forceinline__ void finalize_dist_body(int block, const KfEntry* __restrict__ kfs, int n_kf, int k0, int kc,
+                                                   const QFrame* __restrict__ frames, int n_frames, const uint16_t* __restrict__ scratch,
+                                                   int scratch_stride, lc_kf_result* __restrict__ results, const Knobs& kb) {
   const int lane = threadIdx.x & 31;
-  const int idx = blockIdx.x * kFinWarps + (threadIdx.x >> 5);
+  const int idx = block * kFinWarps + (threadIdx.x >> 5);
   if (idx >= kc * n_frames) return;
   const int f = idx / kc, k = k0 + (idx - f * kc);
   const int item = f * n_kf + k;
@@ -514,44 +514,69 @@ __global__ void __launch_bounds__(kFinWarps * 32)
   }
   if (lane == 0) results[item] = lc_kf_result{kf.frame_id, kf.n, dmin, cnt_good};
 }
+__global__ void __launch_bounds__(kFinWarps * 32)
+    finalize_dist_kernel(const KfEntry* __restrict__ kfs, int n_kf, int k0, int kc, const QFrame* __restrict__ frames, int n_frames,
+                         const uint16_t* __restrict__ scratch, int scratch_stride, lc_kf_result* __restrict__ results, Knobs kb) {
+  finalize_dist_body(blockIdx.x, kfs, n_kf, k0, kc, frames, n_frames, scratch, scratch_stride, results, kb);
+}
 
 // best_packed[i] = dist << 32 | local keyframe index  ->  dist << 32 | global row of the first row of that keyframe
 // at that distance (lowest keyframe, then lowest row: OpenCV's multi-image order).  One warp per query.
-__global__ void __launch_bounds__(256)
-    resolve_best_kernel(const KfEntry* __restrict__ kfs, const QFrame* __restrict__ frames, int n_frames) {
+constexpr int kResolveGroups = 8;
+__device__ __forceinline__ void resolve_best_body(int block, int n_blocks, const KfEntry* __restrict__ kfs, const QFrame* __restrict__ frames,
+                                                  int n_frames) {
   const int lane = threadIdx.x & 31;
   const int wpb = blockDim.x >> 5;
   for (int f = 0; f < n_frames; ++f) {
     const QFrame fr = frames[f];
     if (!fr.best_packed) continue;
-    for (int i = blockIdx.x * wpb + (threadIdx.x >> 5); i < fr.nq; i += gridDim.x * wpb) {
+    for (int i = block * wpb + (threadIdx.x >> 5); i < fr.nq; i += n_blocks * wpb) {
       const uint64_t packed = fr.best_packed[i];
       if (packed == ~0ull) continue;  // nothing was compared
       const int d = (int)(packed >> 32);
       const KfEntry kf = kfs[(uint32_t)packed];
       const uint4 qa = __ldg(fr.q + 2 * (size_t)i), qb = __ldg(fr.q + 2 * (size_t)i + 1);
       int found = -1;
-      for (int j0 = 0; j0 < kf.n && found < 0; j0 += 128) {  // four independent 32-row groups in flight per step
-        uint32_t hit[4];
+      // kResolveGroups independent 32-row groups in flight per step: a step is one L2 round trip, and the steps of a
+      // query are serial (the scan stops at the first hit), so their number is the kernel's latency
+      for (int j0 = 0; j0 < kf.n && found < 0; j0 += 32 * kResolveGroups) {
+        uint32_t hit[kResolveGroups];
+        uint4 a[kResolveGroups], b[kResolveGroups];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const int j = j0 + 32 * u + lane;
-          int dj = -1;
-          if (j < kf.n) {
-            const uint4 a = __ldg(kf.rows + 2 * (size_t)j), b = __ldg(kf.rows + 2 * (size_t)j + 1);
-            dj = __popc(qa.x ^ a.x) + __popc(qa.y ^ a.y) + __popc(qa.z ^ a.z) + __popc(qa.w ^ a.w) + __popc(qb.x ^ b.x) +
-                 __popc(qb.y ^ b.y) + __popc(qb.z ^ b.z) + __popc(qb.w ^ b.w);
-          }
-          hit[u] = __ballot_sync(0xffffffffu, dj == d);
+        for (int u = 0; u < kResolveGroups; ++u) {  // all loads first (rows past the end: the last row again)
+          const int j = min(j0 + 32 * u + lane, kf.n - 1);
+          a[u] = __ldg(kf.rows + 2 * (size_t)j);
+          b[u] = __ldg(kf.rows + 2 * (size_t)j + 1);
         }
 #pragma unroll
-        for (int u = 3; u >= 0; --u)
+        for (int u = 0; u < kResolveGroups; ++u) {
+          const int dj = __popc(qa.x ^ a[u].x) + __popc(qa.y ^ a[u].y) + __popc(qa.z ^ a[u].z) + __popc(qa.w ^ a[u].w) +
+                         __popc(qb.x ^ b[u].x) + __popc(qb.y ^ b[u].y) + __popc(qb.z ^ b[u].z) + __popc(qb.w ^ b[u].w);
+          hit[u] = __ballot_sync(0xffffffffu, dj == d && j0 + 32 * u + lane < kf.n);
+        }
+#pragma unroll
+        for (int u = kResolveGroups - 1; u >= 0; --u)
           if (hit[u]) found = j0 + 32 * u + __ffs(hit[u]) - 1;  // the lowest group wins
       }
       if (found < 0) __trap();  // the distance came from this keyframe: a miss is a kernel bug
       if (lane == 0) fr.best_packed[i] = ((uint64_t)d << 32) | (uint64_t)(kf.global_row_off + found);
     }
   }
+}
+__global__ void __launch_bounds__(256)
+    resolve_best_kernel(const KfEntry* __restrict__ kfs, const QFrame* __restrict__ frames, int n_frames) {
+  resolve_best_body(blockIdx.x, gridDim.x, kfs, frames, n_frames);
+}
+// Both steps after the matching kernel in one launch when all keyframes went through in one batch (they are independent:
+// one reads the distance scratch, the other the per-query bests): blocks [0, n_fin) finalize, the rest resolve.
+static_assert(kFinWarps * 32 == 256, "finish_kernel runs both bodies with 256 threads");
+__global__ void __launch_bounds__(256)
+    finish_kernel(int n_fin, const KfEntry* __restrict__ kfs, int n_kf, const QFrame* __restrict__ frames, int n_frames,
+                  const uint16_t* __restrict__ scratch, int scratch_stride, lc_kf_result* __restrict__ results, Knobs kb) {
+  if ((int)blockIdx.x < n_fin)
+    finalize_dist_body(blockIdx.x, kfs, n_kf, 0, n_kf, frames, n_frames, scratch, scratch_stride, results, kb);
+  else
+    resolve_best_body(blockIdx.x - n_fin, gridDim.x - n_fin, kfs, frames, n_frames);
 }
 
 }  // namespace fx
