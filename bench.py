@@ -43,7 +43,7 @@ POPC_PER_PAIR = 8
 # ncu --set full, lc::fx::mxf4_match_kernel on 4000 keyframes x 2000 rows (profiles/r01_ncu_mxf4_match.txt: 256.6 MB read,
 # 17.7 MB written):
 # dram read + write bytes per keyframe (64,000 B of rows are the algorithmic read; 4,000 B of u16 distances the write)
-TRAFFIC_BYTES_PER_KF = 68_600
+TRAFFIC_BYTES_PER_KF = 68_900
 
 WORKLOADS = {
     "c4": dict(keyframes=100_000, name="C4: 2000-descriptor query vs 100k-keyframe DB (200M rows x 256 bit, 6.4 GB)"),
@@ -417,6 +417,52 @@ def main():
     return 0
 
 
+def c1_sequence(lc, kernel, n_frames=97, cpu_frames=8):
+    """BASELINE config 1 in shape (the reference's own run: ~97 processed frames, ORB 2000, min_loop_gap 30, threshold 0.15)
+    on synthetic descriptors: per frame matchFeatures(prev, cur) + store append + detectLoops(cur), i.e. the calls
+    processFrame makes (include/loop_closing.hpp:34), through the C ABI with host buffers.  ORB detection and the pose
+    stages stay on the host and are not part of it.  The same calls through cv2 on the last `cpu_frames` frames beside it."""
+    import datagen
+    from oracle import cv2_ref
+    from oracle.params import Params
+    frames = [datagen.uniform(2000, 900 + i) for i in range(n_frames)]
+    p = Params(loop_threshold=0.15, min_loop_gap=30)
+
+    def run(c):
+        per = []
+        for i, d in enumerate(frames):
+            t0 = time.perf_counter()
+            if i:
+                c.match_pair(frames[i - 1], d)
+            c.db_append(i, d)
+            c.loop_check(d, i, want_best=False)
+            per.append(time.perf_counter() - t0)
+        return per
+
+    with lc.Context(kernel=kernel, loop_threshold=p.loop_threshold, min_loop_gap=p.min_loop_gap) as c:
+        run(c)  # warm-up pass (buffer growth, first launches)
+    with lc.Context(kernel=kernel, loop_threshold=p.loop_threshold, min_loop_gap=p.min_loop_gap) as c:
+        per = run(c)
+    pair_matches = (n_frames - 1) + sum(max(0, i - 29) for i in range(n_frames))  # consecutive + eligible loop matches
+    out = {"gpu_ms_total": float(np.sum(per) * 1e3), "gpu_us_per_frame_median": float(np.median(per) * 1e6),
+           "gpu_us_last_frame": float(per[-1] * 1e6), "pair_matches": pair_matches,
+           "gpu_gpairs_s": pair_matches * 4e6 / float(np.sum(per)) / 1e9,
+           "api": "lc_match_pair + lc_db_append + lc_loop_check per frame (ctypes, host buffers)"}
+    if cv2_ref.available():
+        import cv2
+        cv2.setNumThreads(os.cpu_count() or 1)
+        t0 = time.perf_counter()
+        n = 0
+        for i in range(n_frames - cpu_frames, n_frames):
+            cv2_ref.match_features(frames[i - 1], frames[i], p)
+            cv2_ref.loop_check(frames[i], frames[:i + 1], list(range(i + 1)), i, p, want_best=False)
+            n += 1 + max(0, i - 29)
+        dt = time.perf_counter() - t0
+        out.update({"cpu_ms_per_frame_last_frames": dt / cpu_frames * 1e3, "cpu_gpairs_s": n * 4e6 / dt / 1e9, "cpu_frames_timed": cpu_frames,
+                    "cpu_cores": os.cpu_count() or 1, "cpu_kind": "cv2.BFMatcher(NORM_HAMMING).match per frame pair (OpenCV %s)" % cv2.__version__})
+    return out
+
+
 def extras(lc, torch, q, kernel):
     """The other single-GPU BASELINE configs, for context (not the headline): C2 pair latency, C3 loop check."""
     import datagen
@@ -440,6 +486,7 @@ def extras(lc, torch, q, kernel):
                                     "kernel_us_median": float(np.median(ks) * 1e3),
                                     "kernel_gpairs_s": 4e6 / (float(np.median(ks)) * 1e-3) / 1e9, "launches_per_call": 1,
                                     "api": "lc_match_pair (C ABI via ctypes, host buffers in and out)"}
+        out["c1_sequence_97_frames"] = c1_sequence(lc, kernel)
         g = torch.Generator(device="cuda")
         g.manual_seed(DB_SEED)
         rows = torch.randint(0, 256, (1000 * 2000, 32), dtype=torch.uint8, device="cuda", generator=g)

@@ -112,7 +112,7 @@ typedef struct lc_timing {
   float d2h_ms;    /* device -> pinned results */
   float total_ms;  /* first H2D to last D2H on the stream */
   int32_t kernel_launches;
-  int32_t path;    /* 1 = whole-keyframe scan kernel, 2 = split kernel + finalize, 3 = int8 tensor-core kernel + finalize, 4 = FP4 tensor-core kernel + finalize + resolve, 5 = single-launch pair kernel (lc_match_pair and friends) */
+  int32_t path;    /* 1 = whole-keyframe scan kernel, 2 = split kernel + finalize, 3 = int8 tensor-core kernel + finalize, 4 = FP4 tensor-core kernel + finalize + resolve, 5 = single-launch pair kernel (lc_match_pair and friends), 6 = SIFT/L2 tensor-core kernel (lc_l2_*) */
   float match_ms;  /* the dominant (matching) kernel alone, summed over its launches of the call */
   int32_t match_launches;
 } lc_timing;

@@ -1482,7 +1482,7 @@ int l2_run(lc_ctx* c, const l2::L2Kf* d_kfs, int n_kf, const l2::L2Frame* d_fram
   LC_CUDA(c, cudaGetLastError());
   c->launches += 2;
   c->timing.kernel_launches += 3;
-  c->timing.path = 5;
+  c->timing.path = 6;
   return LC_OK;
 }
 

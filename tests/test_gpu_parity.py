@@ -77,6 +77,27 @@ def test_pair_shapes_low_entropy_ties(lc, kernel, nq, nt):
         _check_pair(c.match_pair(q, t), q, t)
 
 
+@pytest.mark.parametrize("nq,nt", [(40000, 900),     # results past the direct-to-pinned limit: device buffer + one copy
+                                   (300, 530000),    # rows past the pinned upload buffer: the two-copy staging road
+                                   (70000, 70),      # many query chunks, one short segment each
+                                   (9, 300000)])     # one warp of queries against many full waves of segments
+def test_pair_large_shapes_take_the_other_roads(lc, nq, nt):
+    """the single-launch pair kernel beyond the sizes its fast paths are built for; same context reused afterwards."""
+    q, t = datagen.low_entropy(nq, 3), datagen.uniform(nt, 4)
+    t[nt // 3] = q[0]  # an exact copy: min_dist 0, so the 2 x min filter keeps only distance-0 matches
+    want = c_oracle.match_features(q, t, nthreads=16)
+    with _ctx(lc) as c:
+        for _ in range(2):
+            got = c.match_pair(q, t)
+            assert c.last_timing().path == 5
+            np.testing.assert_array_equal(got["train_idx"], want["train_idx"])
+            np.testing.assert_array_equal(got["dist"], want["dist"])
+            np.testing.assert_array_equal(got["good"], want["good"])
+            assert (got["min_dist"], got["n_good"]) == (want["min_dist"], want["n_good"]) and got["min_dist"] == 0
+        small_q, small_t = datagen.uniform(50, 8), datagen.uniform(60, 9)
+        _check_pair(c.match_pair(small_q, small_t), small_q, small_t)  # the self-cleaning buffers are back at idle
+
+
 @pytest.mark.parametrize("kernel", KERNELS)
 def test_pair_planted_duplicates_filter_bites(lc, kernel):
     q, t = datagen.planted_pair(1500, 1800, 7)
