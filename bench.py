@@ -409,6 +409,19 @@ def main():
     }
     if world == 1 and not args.no_extra:
         line["extra"] = extras(lc, torch, q, kernel)
+        if n_kf >= 1000:  # BASELINE config 5 in shape, on this GPU's resident DB: 64 query frames in one batched check
+            import datagen
+            frames = [q] + [datagen.uniform(NQ, 7000 + i) for i in range(63)]
+            ctx.loop_check_batch(frames[:4], [cur_id] * 4)
+            t0 = time.perf_counter()
+            res, _ = ctx.loop_check_batch(frames, [cur_id] * 64)
+            dt = time.perf_counter() - t0
+            tm = ctx.last_timing()
+            ok = bool(np.array_equal(res[0], r))  # frame 0 is the single check's query: same records expected
+            line["extra"]["c5_batch_64_frames"] = {"e2e_ms": dt * 1e3, "e2e_gpairs_s": 64 * pairs_per_step / dt / 1e9,
+                                                   "match_kernel_ms": tm.match_ms, "match_launches": tm.match_launches,
+                                                   "frame0_records_equal_single_check": ok,
+                                                   "api": "lc_loop_check_batch (C ABI, 64 host query frames in, records + bests out)"}
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(q)
     print(json.dumps(line))
