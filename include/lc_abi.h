@@ -216,6 +216,14 @@ int32_t lc_select_candidates(const lc_ctx* ctx, const lc_kf_result* results, int
 int32_t lc_detect_loops(lc_ctx* ctx, const uint8_t* q, int32_t nq, size_t q_stride, int32_t current_frame_id,
                         lc_loop_candidate* out, int64_t out_cap, int64_t* n_out);
 
+/* Merge step of a keyframe-sharded check (one process per GPU, store created with shard_rank / shard_world): every rank
+ * lets lc_loop_check_batch_device write its records [n_frames][slots] and bests [rows] into ONE contribution buffer
+ * [records | bests] of contrib_bytes (a multiple of 16), all-gathers the contributions (ncclAllGather) and calls this:
+ * records_out[f][slot * world + r] = rank r's record (keyframe k lives on rank k % world, slot k / world) and
+ * best_out[i] = the unsigned minimum over the ranks - one kernel, asynchronous on `cuda_stream`. */
+int32_t lc_merge_shards_device(lc_ctx* ctx, const void* d_gathered, int64_t contrib_bytes, int32_t world, int32_t n_frames,
+                               int64_t slots, int64_t rows, lc_kf_result* d_records_out, uint64_t* d_best_out,
+                               void* cuda_stream);
 /* ---- device-pointer variants: everything already in HBM, asynchronous on `cuda_stream`
  *      (a cudaStream_t; NULL = the context's own non-blocking stream - pass cudaStreamLegacy (0x1) to
  *      mean the legacy default stream).  d_q: contiguous 32-byte rows, 16-byte

@@ -79,6 +79,7 @@ SYMBOLS = {
     "lc_detect_loops": (_i32, [_vp, _vp, _i32, _sz, _i32, _vp, _i64, _pi64]),
     "lc_loop_check_device": (_i32, [_vp, _vp, _i32, _i32, _vp, _vp, _vp]),
     "lc_loop_check_batch_device": (_i32, [_vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "lc_merge_shards_device": (_i32, [_vp, _vp, _i64, _i32, _i32, _i64, _i64, _vp, _vp, _vp]),
     "lc_match_pair_device": (_i32, [_vp, _vp, _i32, _vp, _i32, _vp, _vp, _vp, _vp, _vp]),
     "lc_get_last_timing": (_i32, [_vp, C.POINTER(Timing)]),
     "lc_launch_count": (_i64, [_vp]),
@@ -392,6 +393,10 @@ class Context:
         cur = np.ascontiguousarray(current_frame_ids, np.int32)
         self._ck(self._lib.lc_loop_check_batch_device(self._h, len(nq), d_q, nq.ctypes.data, cur.ctypes.data,
                                                       d_results, d_best, stream))
+
+    def merge_shards_device(self, d_gathered, contrib_bytes, world, n_frames, slots, rows, d_records_out, d_best_out, stream=None):
+        self._ck(self._lib.lc_merge_shards_device(self._h, d_gathered, int(contrib_bytes), int(world), int(n_frames), int(slots),
+                                                  int(rows), d_records_out, d_best_out, stream))
 
     def match_pair_device(self, d_q, nq, d_t, nt, d_idx, d_dist, d_good, d_summary, stream=None):
         self._ck(self._lib.lc_match_pair_device(self._h, d_q, int(nq), d_t, int(nt), d_idx, d_dist, d_good, d_summary, stream))

@@ -1218,6 +1218,29 @@ LC_API int32_t lc_loop_check_batch_device(lc_ctx* c, int32_t n_frames, const voi
   LC_GUARD_END(c)
 }
 
+LC_API int32_t lc_merge_shards_device(lc_ctx* c, const void* d_gathered, int64_t contrib_bytes, int32_t world, int32_t n_frames, int64_t slots,
+                                      int64_t rows, lc_kf_result* d_records_out, uint64_t* d_best_out, void* cuda_stream) {
+  if (!c) return LC_ERR_INVALID;
+  LC_GUARD_BEGIN
+  const int64_t n_rec = (int64_t)n_frames * slots;
+  if (world < 1 || n_frames < 0 || slots < 0 || rows < 0 || contrib_bytes % 16 != 0 || contrib_bytes < n_rec * 16 + rows * 8)
+    return fail(c, LC_ERR_INVALID, "lc_merge_shards_device: bad shape (contribution %lld B for %lld records + %lld bests)",
+                (long long)contrib_bytes, (long long)n_rec, (long long)rows);
+  if ((n_rec > 0 && (!d_gathered || !d_records_out)) || (rows > 0 && (!d_gathered || !d_best_out)))
+    return fail(c, LC_ERR_INVALID, "lc_merge_shards_device: NULL buffer");
+  if (((uintptr_t)d_gathered | (uintptr_t)d_records_out) % 16 != 0) return fail(c, LC_ERR_INVALID, "lc_merge_shards_device: buffers must be 16-byte aligned");
+  if (n_rec * world + rows == 0) return LC_OK;
+  LC_CUDA(c, cudaSetDevice(c->cfg.device));
+  cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : c->stream;
+  const long long items = std::max<long long>(n_rec * world, rows);
+  const int grid = (int)std::min<long long>((items + 255) / 256, 8ll * c->num_sms);
+  merge_shards_kernel<<<grid, 256, 0, st>>>((const uint8_t*)d_gathered, (size_t)contrib_bytes, world, n_rec, rows, (uint4*)d_records_out, d_best_out);
+  LC_CUDA(c, cudaGetLastError());
+  c->launches += 1;
+  return LC_OK;
+  LC_GUARD_END(c)
+}
+
 LC_API int32_t lc_loop_check_device(lc_ctx* c, const void* d_q, int32_t nq, int32_t cur_id, lc_kf_result* d_results,
                                     uint64_t* d_best, void* cuda_stream) {
   return lc_loop_check_batch_device(c, 1, d_q, &nq, &cur_id, d_results, d_best, cuda_stream);

@@ -456,6 +456,26 @@ __global__ void __launch_bounds__(kMaxThreads, 1)
   }
 }
 
+// ---------------------------------------------------------------- sharded merge (multi-GPU)
+// gathered = the all-gathered contributions of `world` ranks, rank r at r * contrib_bytes:
+// [records: n_frames x slots x 16 B | bests: rows x u64].  Out: records[f][slot * world + r] (keyframe k lives on rank
+// k % world in slot k / world) and the unsigned min of the packed bests over the ranks - one launch after one collective.
+__global__ void __launch_bounds__(256)
+    merge_shards_kernel(const uint8_t* __restrict__ gathered, size_t contrib_bytes, int world, long long n_rec_per_rank, long long rows,
+                        uint4* __restrict__ rec_out, uint64_t* __restrict__ best_out) {
+  const long long tid = blockIdx.x * (long long)blockDim.x + threadIdx.x, stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = tid; i < n_rec_per_rank * world; i += stride) {
+    const int r = (int)(i % world);
+    rec_out[i] = __ldg(reinterpret_cast<const uint4*>(gathered + (size_t)r * contrib_bytes) + i / world);
+  }
+  const size_t best_off = (size_t)n_rec_per_rank * 16;
+  for (long long i = tid; i < rows; i += stride) {
+    uint64_t m = ~0ull;
+    for (int r = 0; r < world; ++r) m = min(m, __ldg(reinterpret_cast<const uint64_t*>(gathered + (size_t)r * contrib_bytes + best_off) + i));
+    best_out[i] = m;
+  }
+}
+
 __global__ void fill_u64_kernel(uint64_t* p, size_t n, uint64_t v) {
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) p[i] = v;
 }

@@ -2,10 +2,11 @@
 
 Partitioning: keyframe k lives on rank k % world (append-time round robin), never
 replicated.  A loop check broadcasts nothing but the 64 KB query (every rank already holds it), runs
-the local scan, then does the path's one real exchange:
-    * all_reduce(MIN) of the per-query packed best (dist << 32 | global_row) - an integer min, so the
-      merge is bit-exact and order-independent (NCCL over NVLink/NVSwitch on GPUs);
-    * all_gather of the per-keyframe records, re-interleaved into global keyframe order.
+the local scan, then does the path's one real exchange: every rank's [per-keyframe records | per-query
+packed bests] go round in ONE all_gather (NCCL over NVLink/NVSwitch on GPUs), and one kernel
+(lc_merge_shards_device) re-interleaves the records into global keyframe order and takes the unsigned
+minimum of the packed bests (dist << 32 | global_row) over the ranks - an integer min, so the merge is
+bit-exact and order-independent.
 global_row counts rows of all keyframes in insertion order, so the merged best reproduces OpenCV's
 multi-image tie-break (lowest image, then lowest row) whatever the world size.
 
@@ -54,14 +55,18 @@ class NativeShard:
         self._pin[:t.shape[0]].copy_(t)
         return self._pin[:t.shape[0]].to(self.device, non_blocking=True)
 
-    def loop_check(self, d_q: torch.Tensor, nq, cur_ids, slots):
-        """d_q: (sum nq, 32) uint8 CUDA tensor.  Returns (records int32 [F, slots, 4], best int64 [sum nq])."""
+    def new_buffer(self, nbytes):
+        return torch.empty(int(nbytes), dtype=torch.uint8, device=self.device)
+
+    def loop_check(self, d_q: torch.Tensor, nq, cur_ids, slots, out=None):
+        """d_q: (sum nq, 32) uint8 CUDA tensor.  Returns (records int32 [F, slots, 4], best int64 [sum nq]); `out` =
+        (records, best) tensors to fill instead of new ones (the two halves of a contribution buffer)."""
         F = len(nq)
-        rec = torch.empty((F, slots, 4), dtype=torch.int32, device=self.device)
+        rec = out[0] if out is not None else torch.empty((F, slots, 4), dtype=torch.int32, device=self.device)
         nloc = self.local_keyframes()
         if nloc != slots:
             rec[:, nloc:] = self._sentinel  # this rank holds one keyframe fewer: pad
-        best = torch.empty(int(np.sum(nq)), dtype=torch.int64, device=self.device)
+        best = out[1] if out is not None else torch.empty(int(np.sum(nq)), dtype=torch.int64, device=self.device)
         # one frame: the library's [nloc] records are a prefix of rec[0]; several: it writes [F, nloc] contiguously
         local = torch.empty((F, nloc, 4), dtype=torch.int32, device=self.device) if (nloc != slots and F > 1) else rec
         # NULL means "the context's own stream" in the C ABI; torch's default stream is handle 0, so name it
@@ -73,6 +78,30 @@ class NativeShard:
         if local is not rec and nloc:
             rec[:, :nloc] = local
         return rec, best
+
+    def merge(self, gathered: torch.Tensor, contrib_bytes, world, F, slots, rows):
+        """gathered: the ranks' contribution buffers back to back (uint8).  One kernel: records in global keyframe order
+        [F, slots * world, 4] and the unsigned min of the packed bests [rows]."""
+        rec = torch.empty((F, slots * world, 4), dtype=torch.int32, device=self.device)
+        best = torch.empty(rows, dtype=torch.int64, device=self.device)
+        stream = torch.cuda.current_stream(self.device).cuda_stream or 1
+        self.ctx.merge_shards_device(gathered.data_ptr(), contrib_bytes, world, F, slots, rows, rec.data_ptr() if rec.numel() else None,
+                                     best.data_ptr() if rows else None, stream)
+        return rec, best
+
+
+def merge_torch(gathered: torch.Tensor, contrib_bytes, world, F, slots, rows):
+    """The merge of NativeShard.merge in torch ops, for shard doubles without the library (CPU tests over gloo)."""
+    g = gathered.view(world, contrib_bytes)
+    rec_bytes = F * slots * 16
+    rec = g[:, :rec_bytes].contiguous().view(torch.int32).view(world, F, slots, 4)
+    # [world, F, slots, 4] -> [F, slots, world, 4]: global keyframe k = slot * world + rank
+    merged = rec.permute(1, 2, 0, 3).reshape(F, slots * world, 4)
+    # the packed values are uint64 (UINT64_MAX = "nothing compared on this shard") carried in int64 tensors:
+    # flipping the sign bit makes the signed min the unsigned one
+    best = g[:, rec_bytes:rec_bytes + rows * 8].contiguous().view(torch.int64).view(world, rows)
+    best = ((best ^ _SIGN).min(dim=0).values ^ _SIGN) if rows else best.new_empty(0)
+    return merged, best
 
 
 class ShardedLoopDB:
@@ -139,21 +168,20 @@ class ShardedLoopDB:
 
     def merged_device(self, d_q, nq, cur):
         """Device-resident result of the sharded check: (records int32 [F, slots*world, 4] in global keyframe
-        order (padded with sentinels past K), best int64 [sum nq]).  The exchange happens here."""
+        order (padded with sentinels past K), best int64 [sum nq]).  The exchange happens here: one all_gather of
+        every rank's [records | bests] contribution, then one merge kernel."""
         slots = (self.n_keyframes + self.world - 1) // self.world
-        rec, best = self.shard.loop_check(d_q, nq, cur, slots)
         if self.world == 1:
-            return rec, best
-        if best.numel():
-            # the packed values are uint64 (UINT64_MAX = "nothing compared on this shard") carried in int64 tensors:
-            # flipping the sign bit makes the signed MIN the collectives offer the unsigned min
-            best ^= _SIGN
-            dist.all_reduce(best, op=dist.ReduceOp.MIN, group=self.group)
-            best ^= _SIGN
-        F = rec.shape[0]
-        gathered = torch.empty((self.world * F, slots, 4), dtype=rec.dtype, device=rec.device)
-        dist.all_gather_into_tensor(gathered, rec.contiguous(), group=self.group)
-        gathered = gathered.view(self.world, F, slots, 4)
-        # [world, F, slots, 4] -> [F, slots, world, 4]: global keyframe k = slot * world + rank
-        merged = gathered.permute(1, 2, 0, 3).reshape(rec.shape[0], slots * self.world, 4)
-        return merged, best
+            return self.shard.loop_check(d_q, nq, cur, slots)
+        F, rows = len(nq), int(np.sum(nq))
+        rec_bytes = F * slots * 16
+        contrib_bytes = (rec_bytes + rows * 8 + 15) & ~15
+        new_buffer = getattr(self.shard, "new_buffer", lambda n: torch.empty(int(n), dtype=torch.uint8))
+        contrib = new_buffer(contrib_bytes)
+        rec = contrib[:rec_bytes].view(torch.int32).view(F, slots, 4)
+        best = contrib[rec_bytes:rec_bytes + rows * 8].view(torch.int64)
+        self.shard.loop_check(d_q, nq, cur, slots, out=(rec, best))
+        gathered = new_buffer(self.world * contrib_bytes)
+        dist.all_gather_into_tensor(gathered, contrib, group=self.group)
+        merge = getattr(self.shard, "merge", merge_torch)
+        return merge(gathered, contrib_bytes, self.world, F, slots, rows)

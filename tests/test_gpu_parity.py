@@ -413,6 +413,45 @@ def test_sharded_contexts_merge_equals_single(lc):
         np.testing.assert_array_equal(best, best0)
 
 
+@pytest.mark.parametrize("world", [2, 3, 8])
+def test_merge_shards_kernel_equals_unsharded(lc, world):
+    """the device side of the multi-GPU exchange on ONE GPU: every rank's NativeShard writes its [records | bests]
+    contribution, the buffers are concatenated as the all_gather would leave them, and lc_merge_shards_device must give
+    the unsharded check's answer (and what the torch restatement of the merge gives)."""
+    import torch
+    from slam_loop_closing_b200.sharded import NativeShard, merge_torch
+    p = Params(loop_threshold=0.15, min_loop_gap=10)
+    qs = [datagen.low_entropy(700, 4), datagen.low_entropy(33, 5), np.zeros((0, 32), np.uint8)]  # ties straddle shards
+    curs = [150, 12, 99]  # the second frame sees keyframes 0..2 only: some shards compare nothing (UINT64_MAX bests)
+    kfs = [datagen.low_entropy(int(n), 50 + i) for i, n in enumerate(np.random.default_rng(1).integers(0, 300, 61))]
+    fids = list(range(61))
+    with _ctx(lc, p) as c0:
+        c0.db_append_many(fids, kfs)
+        res0, best0 = c0.loop_check_batch(qs, curs)
+    nq = np.array([len(q) for q in qs], np.int32)
+    F, rows, slots = len(qs), int(nq.sum()), (len(kfs) + world - 1) // world
+    rec_bytes = F * slots * 16
+    contrib_bytes = (rec_bytes + rows * 8 + 15) & ~15
+    shards = [NativeShard(r, world, 0, loop_threshold=p.loop_threshold, min_loop_gap=p.min_loop_gap) for r in range(world)]
+    gathered = torch.zeros(world * contrib_bytes, dtype=torch.uint8, device="cuda")
+    d_q = shards[0].to_device(np.concatenate(qs))
+    for r, sh in enumerate(shards):
+        for k, (fid, kf) in enumerate(zip(fids, kfs)):
+            sh.append(fid, kf if k % world == r else None, len(kf))
+        contrib = gathered[r * contrib_bytes:(r + 1) * contrib_bytes]
+        sh.loop_check(d_q, nq, np.array(curs, np.int32), slots,
+                      out=(contrib[:rec_bytes].view(torch.int32).view(F, slots, 4), contrib[rec_bytes:rec_bytes + rows * 8].view(torch.int64)))
+    rec, best = shards[0].merge(gathered, contrib_bytes, world, F, slots, rows)
+    rec_t, best_t = merge_torch(gathered, contrib_bytes, world, F, slots, rows)
+    torch.cuda.synchronize()
+    assert torch.equal(rec, rec_t) and torch.equal(best, best_t)
+    got = rec.cpu().numpy()[:, :len(kfs)].copy().view(res0.dtype).reshape(F, len(kfs))
+    np.testing.assert_array_equal(got, res0)
+    np.testing.assert_array_equal(best.cpu().numpy().view(np.uint64), np.concatenate(best0))
+    for sh in shards:
+        sh.ctx.close()
+
+
 def test_store_save_load_roundtrip(lc, tmp_path):
     p = Params(min_loop_gap=0)
     q = datagen.uniform(300, 8)

@@ -41,10 +41,14 @@ class OracleShard:
     def to_device(self, rows):
         return torch.from_numpy(np.ascontiguousarray(rows))
 
-    def loop_check(self, d_q, nq, cur_ids, slots):
+    def loop_check(self, d_q, nq, cur_ids, slots, out=None):
         F = len(nq)
         rec = torch.tensor([-1, 0, -1, -1], dtype=torch.int32).repeat(F, slots, 1)
         best = torch.full((int(np.sum(nq)),), -1, dtype=torch.int64)
+        if out is not None:  # fill the caller's contribution buffer halves
+            out[0].copy_(rec)
+            out[1].copy_(best)
+            rec, best = out
         rows = d_q.numpy()
         off = 0
         for f in range(F):

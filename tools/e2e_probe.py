@@ -37,11 +37,16 @@ for _ in range(n):
     t = time.perf_counter()
     nq = np.array([len(q)], np.int32)
     d_q = db.shard.to_device(q); t = lap("to_device", t)
-    rec, best = db.shard.loop_check(d_q, nq, np.array([cur], np.int32), (db.n_keyframes + world - 1) // world); t = lap("shard.loop_check (kernels)", t)
-    best ^= -(1 << 63); dist.all_reduce(best, op=dist.ReduceOp.MIN); best ^= -(1 << 63); t = lap("xor + all_reduce + xor", t)
-    g = torch.empty((world, rec.shape[1], 4), dtype=rec.dtype, device=dev)
-    dist.all_gather_into_tensor(g, rec.contiguous()); t = lap("all_gather", t)
-    merged = g.view(world, 1, -1, 4).permute(1, 2, 0, 3).reshape(1, -1, 4); t = lap("permute copy", t)
+    slots = (db.n_keyframes + world - 1) // world
+    rec_bytes = slots * 16
+    contrib_bytes = (rec_bytes + int(nq.sum()) * 8 + 15) & ~15
+    contrib = db.shard.new_buffer(contrib_bytes)
+    rec = contrib[:rec_bytes].view(torch.int32).view(1, slots, 4)
+    best = contrib[rec_bytes:rec_bytes + int(nq.sum()) * 8].view(torch.int64)
+    db.shard.loop_check(d_q, nq, np.array([cur], np.int32), slots, out=(rec, best)); t = lap("shard.loop_check (kernels)", t)
+    g = db.shard.new_buffer(world * contrib_bytes)
+    dist.all_gather_into_tensor(g, contrib); t = lap("all_gather [records | bests]", t)
+    merged, best = db.shard.merge(g, contrib_bytes, world, 1, slots, int(nq.sum())); t = lap("merge kernel", t)
     r_h, b_h = db._to_host(merged.reshape(-1), best); t = lap("D2H + sync", t)
     out = r_h.view(np.int32).reshape(1, -1, 4)[:, :K].copy(); t = lap("numpy copy", t)
 if rank == 0:
