@@ -251,7 +251,7 @@ def main():
     kernel = {"auto": lc.KERNEL_AUTO, "popc": lc.KERNEL_POPC, "csa": lc.KERNEL_CSA, "tensor": lc.KERNEL_TENSOR, "mxf4": lc.KERNEL_MXF4}[args.kernel]
     cur_id = n_kf + 29  # every keyframe is at least min_loop_gap back
     q = query_rows()
-    db = ShardedLoopDB(device=local, loop_threshold=0.15, kernel=kernel)
+    db = ShardedLoopDB(device=local, loop_threshold=0.15, kernel=kernel, timing=1)  # every check event-timed (match_ms feeds the roofline)
     ctx = db.shard.ctx
     q_dev = db.shard.to_device(q)
     torch.cuda.synchronize()

@@ -224,12 +224,13 @@ int slab_alloc(lc_ctx* c, int64_t n, uint4** out) {
 }
 
 // host rows (any stride) -> device `dst` through the two pinned halves: the CPU packs one half while
-// the copy engine drains the other
+// the copy engine drains the other (every user of a half waits for that half's event first)
 int upload_rows(lc_ctx* c, uint8_t* dst, const uint8_t* src, int64_t n, size_t stride) {
   const int64_t half_rows = (int64_t)(kPinHalfBytes / LC_DESC_BYTES);
   for (int64_t done = 0; done < n;) {
     uint8_t* half = c->pin_up + (size_t)c->pin_half * kPinHalfBytes;
     const int64_t take = std::min(half_rows, n - done);
+    LC_CUDA(c, cudaEventSynchronize(c->pin_ev[c->pin_half]));  // the last copy out of this half has drained
     if (stride == LC_DESC_BYTES) {
       memcpy(half, src + (size_t)done * LC_DESC_BYTES, (size_t)take * LC_DESC_BYTES);
     } else {
@@ -240,7 +241,6 @@ int upload_rows(lc_ctx* c, uint8_t* dst, const uint8_t* src, int64_t n, size_t s
                                cudaMemcpyHostToDevice, c->stream));
     LC_CUDA(c, cudaEventRecord(c->pin_ev[c->pin_half], c->stream));
     c->pin_half ^= 1;
-    LC_CUDA(c, cudaEventSynchronize(c->pin_ev[c->pin_half]));  // the half we fill next has drained
     done += take;
   }
   return LC_OK;
