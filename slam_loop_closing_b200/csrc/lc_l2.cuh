@@ -14,9 +14,11 @@
 //
 // Shape: M = 128 queries x N = 128 train rows x K = 128 bytes (4 MMAs of K = 32) per tile, four 128-column s32
 // accumulators (all of TMEM); up to 1024 resident queries per CTA; train rows go to shared memory as they are (a
-// 128-byte row is one SWIZZLE_128B row), together with their 128 scan constants.  The epilogue's top-2 update costs
-// 2.5 alu instructions per pair against 0.5 for the Hamming maximum, so this kernel is bound by the alu pipe
-// (about 640 cycles per tile against the MMA's 256).
+// 128-byte row is one SWIZZLE_128B row), together with their 128 scan constants.  A streaming top-2 update costs
+// 2.5 alu instructions per pair (against 0.5 for the Hamming maximum) and bound the first version of this kernel at
+// about 640 cycles per tile against the MMA's 256; the epilogue is therefore a tournament: the minimum of every aligned
+// group of 8 columns, the two smallest of the group minima (0.8 alu instructions per pair), and the 7 other rows of the
+// single best group rescanned once per (query, view) at the end.
 #pragma once
 #include "lc_mxf4.cuh"
 
@@ -139,7 +141,12 @@ struct Top2 {
     m2 = min(m2, min(t, hi));
   }
 };
-// running two nearest rows of one query inside one view, in (distance, row) order
+__device__ __forceinline__ int group_min8(int k0, int k1, int k2, int k3, int k4, int k5, int k6, int k7) {
+  return min(min(min(k0, min(k1, k2)), min(k3, k4)), min(min(k5, k6), k7));  // VIMNMX3 x 3 + VIMNMX
+}
+// running two nearest rows of one query inside one view, in (distance, row) order.  While the scan runs, d2 is the nearest
+// row OUTSIDE the aligned group of 8 rows that holds the best one (see the tournament in the epilogue): every merge rule below
+// holds for that meaning as well, because a losing side contributes its overall minimum and a winning side brings its own group.
 struct Knn2 {
   int d1, i1, d2;
   __device__ __forceinline__ void reset() { d1 = d2 = kNoD2, i1 = -1; }
@@ -165,6 +172,33 @@ struct Knn2 {
     }
   }
 };
+
+// smallest distance part |t|^2 - 2 q.t among the rows of the aligned group of 8 around row i1 of a view, i1 itself excluded
+// (kNoD2 if there is none): 7 dot products of 128 bytes, once per (query, view)
+__device__ __forceinline__ int rescan_group(const uint4* __restrict__ qrow, const L2Kf& kf, int i1) {
+  uint4 q[8];
+#pragma unroll
+  for (int w = 0; w < 8; ++w) q[w] = __ldg(qrow + w);
+  const int base = i1 & ~7;
+  int best = kNoD2;
+#pragma unroll 1
+  for (int r = 0; r < 8; ++r) {
+    const int j = base + r;
+    if (j >= kf.n || j == i1) continue;
+    const uint4* t = kf.rows + (size_t)j * 8;
+    unsigned dot = 0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) {
+      const uint4 v = __ldg(t + w);
+      dot = __dp4a(q[w].x, v.x, dot);
+      dot = __dp4a(q[w].y, v.y, dot);
+      dot = __dp4a(q[w].z, v.z, dot);
+      dot = __dp4a(q[w].w, v.w, dot);
+    }
+    best = min(best, (int)__ldg(kf.norms + j) - 2 * (int)dot);
+  }
+  return best;
+}
 
 // One CTA per CtaWork entry: query block `ablock` against views k0 + slot, k0 + slot + n_slots, ...
 __global__ void __launch_bounds__(kThreads, 1)
@@ -337,15 +371,26 @@ __global__ void __launch_bounds__(kThreads, 1)
             tmem_ld32(tmem_rows + st * kTN + 32, b);
             tmem_ld_wait();
             fx::release_stage(acc_empty + 8 * st);
+            // Tournament: the minimum of every aligned group of 8 columns (4 min3/min per 8 keys), then the two smallest
+            // of the 8 group minima.  m1 is the half-tile's smallest key; m2 is the smallest key OUTSIDE m1's group - the
+            // other 7 keys of that one group are looked at once per (query, view) at the very end (rescan_group), not here.
             Top2 t2;
             t2.reset();
 #pragma unroll
-            for (int j = 0; j < 32; j += 4) {  // key = -256 * dot + (|t|^2 * 128 + column)
-              const int4 ka = kc4[j >> 2], kbv = kc4[8 + (j >> 2)];
-              t2.push2(a[j] * -256 + ka.x, a[j + 1] * -256 + ka.y);
-              t2.push2(a[j + 2] * -256 + ka.z, a[j + 3] * -256 + ka.w);
-              t2.push2(b[j] * -256 + kbv.x, b[j + 1] * -256 + kbv.y);
-              t2.push2(b[j + 2] * -256 + kbv.z, b[j + 3] * -256 + kbv.w);
+            for (int j = 0; j < 32; j += 16) {  // key = -256 * dot + (|t|^2 * 128 + column)
+              int g[4];
+#pragma unroll
+              for (int u = 0; u < 2; ++u) {
+                const int4 k0 = kc4[(j >> 2) + 2 * u], k1 = kc4[(j >> 2) + 2 * u + 1];
+                const int4 k2 = kc4[8 + (j >> 2) + 2 * u], k3 = kc4[8 + (j >> 2) + 2 * u + 1];
+                const int c = j + 8 * u;
+                g[u] = group_min8(a[c] * -256 + k0.x, a[c + 1] * -256 + k0.y, a[c + 2] * -256 + k0.z, a[c + 3] * -256 + k0.w,
+                                  a[c + 4] * -256 + k1.x, a[c + 5] * -256 + k1.y, a[c + 6] * -256 + k1.z, a[c + 7] * -256 + k1.w);
+                g[2 + u] = group_min8(b[c] * -256 + k2.x, b[c + 1] * -256 + k2.y, b[c + 2] * -256 + k2.z, b[c + 3] * -256 + k2.w,
+                                      b[c + 4] * -256 + k3.x, b[c + 5] * -256 + k3.y, b[c + 6] * -256 + k3.z, b[c + 7] * -256 + k3.w);
+              }
+              t2.push2(g[0], g[1]);
+              t2.push2(g[2], g[3]);
             }
             // tile-local (distance part, column) -> running neighbours; rows of later tiles are higher
             const int e1 = t2.m1 >> 7, j1 = row0 + (t2.m1 & 127), e2 = t2.m2 >> 7;
@@ -376,8 +421,17 @@ __global__ void __launch_bounds__(kThreads, 1)
           r.merge_any(x[0], x[1], x[2]);
           // distance parts -> squared distances; a pad column's part (>= kNone >> 7) means "no such row"
           const int limit = kNone >> 7;
-          const int d1 = r.d1 >= limit ? kNoD2 : r.d1 + na[j], d2 = r.d2 >= limit ? kNoD2 : r.d2 + na[j];
-          const bool g = ratio_test(d1, d2, kb.ratio);
+          const int d1 = r.d1 >= limit ? kNoD2 : r.d1 + na[j];
+          int d2 = r.d2 >= limit ? kNoD2 : r.d2 + na[j];
+          // so far d2 is the nearest row OUTSIDE the best row's group of 8; the 7 rows inside it are the last candidates.
+          // They can only lower d2, so a ratio test that already fails stays failed: the rescan is needed only for the
+          // queries that pass so far (few, except against a view of the same place) and when the caller wants d2 itself.
+          bool g = ratio_test(d1, d2, kb.ratio);
+          if (d1 != kNoD2 && (g || d2 == kNoD2 || fr.d2 != nullptr)) {  // (no row outside the group at all: it decides alone)
+            const int e = rescan_group(fr.q + (size_t)(ab.q0 + ql) * 8, kf, r.i1);
+            if (e != kNoD2) d2 = min(d2, e + na[j]);
+            g = ratio_test(d1, d2, kb.ratio);
+          }
           cnt_good += g ? 1 : 0;
           const int q = ab.q0 + ql;
           if (fr.train_idx) fr.train_idx[q] = d1 == kNoD2 ? -1 : r.i1;

@@ -110,6 +110,46 @@ def test_l2_loop_check_many_views_vs_oracle(lc):
     assert (res["n_good"][:211:9][big[:211:9]] > 100).all()  # the overlapping views stand out
 
 
+def test_l2_second_neighbour_inside_and_outside_the_best_rows_group(lc):
+    """the kernel ranks aligned groups of 8 train rows first and looks inside the best group only when the ratio test can
+    still pass: views whose two nearest rows sit in one group, straddle a group boundary, or ARE the whole view
+    (n <= 8), through the loop check (counts only) and the pair API (exact second distance)."""
+    rng = np.random.default_rng(11)
+    q = rng.integers(0, 200, (600, 128)).astype(np.uint8)
+
+    def near(rows, amp):
+        return np.clip(rows.astype(np.int32) + rng.integers(-amp, amp + 1, rows.shape), 0, 255).astype(np.uint8)
+
+    views = []
+    for n in (3, 8, 9, 130, 700, 700, 700, 1500):
+        views.append(rng.integers(0, 200, (n, 128)).astype(np.uint8))
+    views[0][:2] = near(q[:2], 1)                      # the whole view is one (partial) group
+    views[1][:8] = near(q[:8], 1)                      # exactly one full group
+    views[2][7], views[2][8] = near(q[5:6], 1)[0], near(q[5:6], 2)[0]   # nearest and second straddle rows 7 | 8
+    for v, amp2 in ((views[4], 1), (views[5], 3), (views[6], 40)):
+        for i in range(0, 300, 3):                     # nearest at row 2i + 100, second right beside it (same group or next)
+            v[2 * i + 100] = near(q[i:i + 1], 1)[0]
+            v[2 * i + 101] = near(q[i:i + 1], amp2)[0]
+    views[7][::2][:600] = near(q, 2)                   # a well-separated nearest row for every query: most pass
+    with lc.Context() as c:
+        for k, v in enumerate(views):
+            c.l2_db_append(k, v)
+        for ratio in (0.7, 0.95):
+            res = c.l2_loop_check(q, 100, 1, ratio, 1)
+            want = l2_oracle.loop_check(q, views, list(range(len(views))), 100, 1, ratio, 1, nthreads=16)
+            np.testing.assert_array_equal(res, want)
+        assert res["n_good"][7] > 400 and res["n_good"][4] < res["n_good"][6]
+        for v in views:
+            r = c.l2_match_pair(q, v, 0.8)
+            w = l2_oracle.match_features(q, v, 0.8, nthreads=16)
+            np.testing.assert_array_equal(r["train_idx"], w["train_idx"])
+            np.testing.assert_array_equal(r["distance"], w["distance"])
+            np.testing.assert_array_equal(r["good"], w["good"])
+            has2 = w["second_dist2"] >= 0  # the exact second distance, whichever side of the group boundary it came from
+            np.testing.assert_array_equal(r["second"][has2], np.sqrt(w["second_dist2"][has2].astype(np.float32)))
+            assert (r["second"][~has2] == -1).all()
+
+
 def test_l2_rejects_non_sift_values(lc):
     with lc.Context() as c:
         with pytest.raises(lc.LcError):
