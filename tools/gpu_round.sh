@@ -17,3 +17,8 @@ ncu --set full --clock-control none --import-source on -k regex:mxf4_match -s 3 
   python tools/tc_probe.py 0 4000 > gpurun_out/${TAG}_ncu2.log 2>&1
 echo "full capture rc=$?"
 cat gpurun_out/${TAG}_probe.log
+python tools/l2_probe.py 400 > gpurun_out/${TAG}_l2probe.log 2>&1 && \
+ncu --set full --clock-control none --import-source on -k regex:l2_match -s 1 -c 1 -f -o gpurun_out/${TAG}_l2 \
+  python tools/l2_probe.py 400 > gpurun_out/${TAG}_ncu3.log 2>&1
+echo "l2 capture rc=$?"
+cat gpurun_out/${TAG}_l2probe.log
