@@ -72,6 +72,9 @@ struct lc_ctx {
   uint8_t* pin_up = nullptr;  // 2 x kPinHalfBytes
   int pin_half = 0;
   uint8_t* pin_down = nullptr;
+  uint8_t* pin_loop = nullptr;      // loop-check results (may be pending while other calls use pin_down)
+  uint8_t* pin_loop_dev = nullptr;
+  size_t pin_loop_cap = 0;
   uint8_t* pin_down_dev = nullptr;  // the same buffer as the device addresses it (results stored by kernels directly)
   size_t pin_down_cap = 0;
   DevBuf d_q, d_t, d_results, d_scratch, d_frames, d_pairkeys, d_paircnt, d_out, d_counter, d_qimg, d_ablocks;
@@ -150,20 +153,25 @@ int ensure(lc_ctx* c, DevBuf& b, size_t bytes) {
   return LC_OK;
 }
 
-int ensure_pin_down(lc_ctx* c, size_t bytes) {
-  if (bytes <= c->pin_down_cap) return LC_OK;
-  if (c->pin_down) {
+int ensure_pinned(lc_ctx* c, uint8_t*& host, uint8_t*& dev, size_t& cap, size_t bytes) {
+  if (bytes <= cap) return LC_OK;
+  if (host) {
     LC_CUDA(c, cudaStreamSynchronize(c->stream));
-    LC_CUDA(c, cudaFreeHost(c->pin_down));
-    c->pin_down = nullptr;
-    c->pin_down_cap = 0;
+    LC_CUDA(c, cudaFreeHost(host));
+    host = dev = nullptr;
+    cap = 0;
   }
-  size_t ncap = std::max(bytes, c->pin_down_cap * 2);
-  LC_CUDA(c, cudaHostAlloc((void**)&c->pin_down, ncap, cudaHostAllocMapped));
-  LC_CUDA(c, cudaHostGetDevicePointer((void**)&c->pin_down_dev, c->pin_down, 0));
-  c->pin_down_cap = ncap;
+  size_t ncap = std::max(bytes, cap * 2);
+  LC_CUDA(c, cudaHostAlloc((void**)&host, ncap, cudaHostAllocMapped));
+  LC_CUDA(c, cudaHostGetDevicePointer((void**)&dev, host, 0));
+  cap = ncap;
   return LC_OK;
 }
+// results of the synchronous host-buffer calls
+int ensure_pin_down(lc_ctx* c, size_t bytes) { return ensure_pinned(c, c->pin_down, c->pin_down_dev, c->pin_down_cap, bytes); }
+// results of a loop check: a buffer of its own, because between lc_loop_check_begin and lc_loop_check_end the caller may
+// make other calls (the next frame's pair match) that land their results in pin_down
+int ensure_pin_loop(lc_ctx* c, size_t bytes) { return ensure_pinned(c, c->pin_loop, c->pin_loop_dev, c->pin_loop_cap, bytes); }
 
 // bracket the launches of the matching kernel with events while a host-buffer call is being timed
 struct MatchTimer {
@@ -830,6 +838,7 @@ LC_API void lc_destroy(lc_ctx* c) {
     if (b->p) cudaFree(b->p);
   if (c->pin_up) cudaFreeHost(c->pin_up);
   if (c->pin_down) cudaFreeHost(c->pin_down);
+  if (c->pin_loop) cudaFreeHost(c->pin_loop);
   for (auto& e : c->ev) if (e) cudaEventDestroy(e);
   for (auto& e : c->pin_ev) if (e) cudaEventDestroy(e);
   for (auto& e : c->match_ev) if (e) cudaEventDestroy(e);
@@ -1270,7 +1279,7 @@ int loop_check_enqueue_impl(lc_ctx* c, int32_t n_frames, const uint8_t* const* q
   const size_t res_bytes = (size_t)c->pending.n_res * sizeof(lc_kf_result), best_bytes = want_best ? (size_t)rows * 8 : 0;
   LC_TRY(ensure(c, c->d_q, row_bytes + table_bytes));
   LC_TRY(ensure(c, c->d_results, std::max<size_t>(res_bytes + best_bytes, 16)));
-  LC_TRY(ensure_pin_down(c, res_bytes + best_bytes + 16));
+  LC_TRY(ensure_pin_loop(c, res_bytes + best_bytes + 16));
   lc_kf_result* d_results = (lc_kf_result*)c->d_results.p;
   uint64_t* d_best = want_best ? (uint64_t*)((uint8_t*)c->d_results.p + res_bytes) : nullptr;  // res_bytes is a multiple of 16
   std::vector<QFrame> hf;
@@ -1300,7 +1309,7 @@ int loop_check_enqueue_impl(lc_ctx* c, int32_t n_frames, const uint8_t* const* q
   if (c->timing_on) LC_CUDA(c, cudaEventRecord(c->ev[1], c->stream));
   LC_TRY(loop_check_run(c, c->stream, hf, d_frames, rows_built, d_results, d_best));
   if (c->timing_on) LC_CUDA(c, cudaEventRecord(c->ev[2], c->stream));
-  if (res_bytes + best_bytes) LC_CUDA(c, cudaMemcpyAsync(c->pin_down, c->d_results.p, res_bytes + best_bytes, cudaMemcpyDeviceToHost, c->stream));
+  if (res_bytes + best_bytes) LC_CUDA(c, cudaMemcpyAsync(c->pin_loop, c->d_results.p, res_bytes + best_bytes, cudaMemcpyDeviceToHost, c->stream));
   if (c->timing_on) LC_CUDA(c, cudaEventRecord(c->ev[3], c->stream));
   c->pending.res_bytes = res_bytes;
   c->pending.best_bytes = best_bytes;
@@ -1327,8 +1336,8 @@ int loop_check_collect(lc_ctx* c, lc_kf_result* results, int64_t results_cap, ui
   if (p.n_res > 0 && (!results || results_cap < p.n_res))
     return fail(c, LC_ERR_CAPACITY, "results_cap %lld < %lld", (long long)results_cap, (long long)p.n_res);
   if (best_packed && p.rows > 0 && !p.best_bytes && p.queued) return fail(c, LC_ERR_INVALID, "the pending check was started without want_best");
-  if (p.res_bytes) memcpy(results, c->pin_down, p.res_bytes);
-  if (p.best_bytes && best_packed) memcpy(best_packed, c->pin_down + p.res_bytes, p.best_bytes);
+  if (p.res_bytes) memcpy(results, c->pin_loop, p.res_bytes);
+  if (p.best_bytes && best_packed) memcpy(best_packed, c->pin_loop + p.res_bytes, p.best_bytes);
   return LC_OK;
 }
 

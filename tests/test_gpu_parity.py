@@ -376,6 +376,29 @@ def test_loop_check_begin_end_overlaps_host_work(lc):
         assert best2 is None and len(res2) == 600
 
 
+def test_other_calls_between_loop_check_begin_and_end(lc):
+    """the streamed front-end in use: while a loop check is pending the caller matches the NEXT pair of frames, appends a
+    keyframe and fetches match lists - none of it may disturb the pending check's results (their pinned buffer is its own)."""
+    p = Params(loop_threshold=0.15, min_loop_gap=30)
+    q = datagen.uniform(2000, 31)
+    kfs = datagen.structured_db(q, 300, n=700, every=7, ragged=True)
+    nxt, nxt2 = datagen.uniform(1800, 32), datagen.uniform(1900, 33)
+    with _ctx(lc, p) as c:
+        c.db_append_many(list(range(300)), kfs)
+        want_res, want_best = c.loop_check(q, 400)
+        c.loop_check_begin(q, 400)
+        _check_pair(c.match_pair(nxt, nxt2), nxt, nxt2)          # results land in the synchronous calls' buffer
+        _check_pair(c.match_vs_keyframe(nxt, 5), nxt, kfs[5])
+        ml = c.match_keyframes(nxt, [0, 7])
+        assert len(ml) == 2
+        assert c.db_append(300, nxt) == 300                       # not part of the pending check
+        res, best = c.loop_check_end()
+        np.testing.assert_array_equal(res, want_res)
+        np.testing.assert_array_equal(best, want_best)
+        res3, _ = c.loop_check(q, 400)                            # the appended keyframe shows up in the next one
+        assert len(res3) == 301 and np.array_equal(res3[:300], want_res)
+
+
 def test_plain_c_client_finds_its_loop(lc, tmp_path):
     """examples/abi_client.c: the C ABI driven from plain C99 - no Python, torch or OpenCV between caller and library."""
     import os
