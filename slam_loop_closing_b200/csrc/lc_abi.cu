@@ -510,7 +510,7 @@ int run_match(lc_ctx* c, cudaStream_t st, const KfEntry* d_kfs, int n_kf, int ma
           }
           LC_CUDA(c, cudaGetLastError());
           finalize_kernel<<<kc * n_frames, 256, 0, st>>>(d_kfs, n_kf, k0, kc, d_frames, (const uint32_t*)c->d_scratch.p, stride,
-                                                         d_results, nullptr, nullptr, nullptr, nullptr, kb);
+                                                         d_results, kb);
         }
         LC_CUDA(c, cudaGetLastError());
         c->launches += 2;
@@ -585,8 +585,7 @@ int run_match(lc_ctx* c, cudaStream_t st, const KfEntry* d_kfs, int n_kf, int ma
       c->launches += 1;
       c->timing.kernel_launches += 1;
     }
-    finalize_kernel<<<nb, 256, 0, st>>>(d_kfs, n_kf, k0, kc, d_frames, (const uint32_t*)c->d_scratch.p, stride, d_results,
-                                        nullptr, nullptr, nullptr, nullptr, kb);
+    finalize_kernel<<<nb, 256, 0, st>>>(d_kfs, n_kf, k0, kc, d_frames, (const uint32_t*)c->d_scratch.p, stride, d_results, kb);
     LC_CUDA(c, cudaGetLastError());
     c->launches += 1;
     c->timing.kernel_launches += 1;

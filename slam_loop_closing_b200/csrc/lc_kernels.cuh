@@ -19,8 +19,10 @@
 //     tie-break; two rows are folded per VIMNMX3.
 //   * Whole-keyframe "scan" kernel: persistent CTAs pull (query frame, keyframe) items from an atomic
 //     counter; the per-keyframe reduction (min, 2xmin filter, count) is fused in the epilogue.
-//   * "Split" kernel for few keyframes (single pair, short DBs): grid over (row segment, item, query
-//     chunk), atomicMin of the key into scratch, then a tiny finalize kernel.
+//   * "Split" kernel for the shortest DBs: grid over (row segment, item, query chunk), atomicMin of the key
+//     into scratch, then a tiny finalize kernel.
+//   * "Pair" kernel for matchFeatures: the split grid with the finalize step (2 x min filter, per-query outputs)
+//     done by the CTA that finishes last - one launch per match.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -326,12 +328,9 @@ __global__ void __launch_bounds__(kMaxThreads, 1)
 }
 
 // one CTA per (frame, keyframe in [k0, k0 + kc)): reduce the scratch keys of one match; results[frame * n_kf + k].
-// Optional per-query outputs (pair API): train_idx, dist, good; summary = {min_dist, n_good}.
 __global__ void __launch_bounds__(256)
     finalize_kernel(const KfEntry* __restrict__ kfs, int n_kf, int k0, int kc, const QFrame* __restrict__ frames,
-                    const uint32_t* __restrict__ scratch, int scratch_stride, lc_kf_result* __restrict__ results,
-                    int32_t* __restrict__ train_idx, int32_t* __restrict__ dist, uint8_t* __restrict__ good,
-                    int32_t* __restrict__ summary, Knobs kb) {
+                    const uint32_t* __restrict__ scratch, int scratch_stride, lc_kf_result* __restrict__ results, Knobs kb) {
   __shared__ int red[8];
   const int f = blockIdx.x / kc, k = k0 + (blockIdx.x - f * kc);
   const int item = f * n_kf + k;
@@ -339,10 +338,7 @@ __global__ void __launch_bounds__(256)
   const KfEntry kf = kfs[k];
   const int tid = threadIdx.x;
   if (!kf_eligible(fr.cur_id, kf.frame_id, kb) || kf.n <= 0 || fr.nq <= 0) {
-    if (tid == 0) {
-      if (results) results[item] = lc_kf_result{kf.frame_id, kf.n, -1, -1};
-      if (summary) { summary[0] = -1; summary[1] = 0; }
-    }
+    if (tid == 0) results[item] = lc_kf_result{kf.frame_id, kf.n, -1, -1};
     return;
   }
   const uint32_t* keys = scratch + (size_t)blockIdx.x * scratch_stride;
@@ -354,19 +350,11 @@ __global__ void __launch_bounds__(256)
   int cnt_good = 0;
   for (int i = tid; i < fr.nq; i += blockDim.x) {
     const uint32_t key = keys[i];
-    const int d = (int)(key >> kKeyShift);
-    const bool g = is_good(d, thr, kb);
-    cnt_good += g ? 1 : 0;
-    if (train_idx) train_idx[i] = (int32_t)(key & kKeyRowMask);
-    if (dist) dist[i] = d;
-    if (good) good[i] = g ? 1 : 0;
+    cnt_good += is_good((int)(key >> kKeyShift), thr, kb) ? 1 : 0;
     if (fr.best_packed) publish_best(fr.best_packed, i, key, kf.global_row_off);
   }
   cnt_good = block_sum(cnt_good, red);
-  if (tid == 0) {
-    if (results) results[item] = lc_kf_result{kf.frame_id, kf.n, dmin, cnt_good};
-    if (summary) { summary[0] = dmin; summary[1] = cnt_good; }
-  }
+  if (tid == 0) results[item] = lc_kf_result{kf.frame_id, kf.n, dmin, cnt_good};
 }
 
 // ---------------------------------------------------------------- pair kernel (matchFeatures): one launch
