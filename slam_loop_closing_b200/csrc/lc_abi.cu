@@ -373,7 +373,22 @@ int run_match(lc_ctx* c, cudaStream_t st, const KfEntry* d_kfs, int n_kf, int ma
   const int kern = c->cfg.kernel;
   const bool want_fp4 = kern == LC_KERNEL_MXF4 || kern == LC_KERNEL_AUTO, want_i8 = kern == LC_KERNEL_TENSOR;
   if ((want_fp4 || want_i8) && max_nq > 0 && max_rows > 0) {
-    const int q_per_cta = want_fp4 ? fx::kQPerCta : tc::kQPerCta;
+    // Queries per block.  int8 path: always 512.  FP4 path: 128 x T, T = 8 resident tiles when there are plenty of
+    // keyframes; for small stores the T in {8, 4, 2} whose (block, keyframe) units fill the SMs in the fewest tile-times
+    // (waves x T: 30 keyframes x 2 blocks of 1024 queries keep 60 SMs busy for 8 tile-times each, 4 blocks of 512 keep 120 busy
+    // for 4).  T = 1 is left out: the four expander warps cannot deliver a train tile per MMA tile.
+    int q_per_cta = want_fp4 ? fx::kQPerCta : tc::kQPerCta;
+    if (want_fp4) {
+      long long best_cost = -1;
+      for (int T = fx::kQTilesPerCta; T >= 2; T >>= 1) {
+        long long n_blocks = 0;
+        for (int f = 0; f < n_frames; ++f) n_blocks += (h_frames[f].nq + T * fx::kQTile - 1) / (T * fx::kQTile);
+        const long long waves = (n_blocks * n_kf + c->num_sms - 1) / c->num_sms;
+        const long long cost = waves * T;
+        // a smaller T re-expands every train tile for fewer queries: it has to win by 10 % to be taken
+        if (best_cost < 0 || cost * 10 < best_cost * 9) best_cost = cost, q_per_cta = T * fx::kQTile;
+      }
+    }
     const size_t img_bytes = want_fp4 ? (size_t)fx::kABytes : (size_t)tc::kABytes;
     std::vector<tc::ABlock> blocks;  // fx::ABlock has the same layout
     static_assert(sizeof(tc::ABlock) == sizeof(fx::ABlock), "ABlock layouts differ");
@@ -381,8 +396,9 @@ int run_match(lc_ctx* c, cudaStream_t st, const KfEntry* d_kfs, int n_kf, int ma
     long long total_tiles = 0;
     for (int f = 0; f < n_frames; ++f)
       for (int q0 = 0; q0 < h_frames[f].nq; q0 += q_per_cta) {
-        blocks.push_back(tc::ABlock{nullptr, f, q0});
-        tiles.push_back((std::min(q_per_cta, h_frames[f].nq - q0) + tc::kQTile - 1) / tc::kQTile);
+        const int nq_blk = std::min(q_per_cta, h_frames[f].nq - q0);
+        blocks.push_back(tc::ABlock{nullptr, f, q0, nq_blk, 0});
+        tiles.push_back((nq_blk + tc::kQTile - 1) / tc::kQTile);
         total_tiles += tiles.back();
       }
     const int n_ab = (int)blocks.size();
@@ -1482,7 +1498,7 @@ int l2_run(lc_ctx* c, const l2::L2Kf* d_kfs, int n_kf, const l2::L2Frame* d_fram
   long long total_tiles = 0;
   for (int f = 0; f < n_frames; ++f)
     for (int q0 = 0; q0 < h_frames[f].nq; q0 += l2::kQPerCta) {
-      blocks.push_back(l2::ABlock{nullptr, f, q0});
+      blocks.push_back(l2::ABlock{nullptr, f, q0, std::min(l2::kQPerCta, h_frames[f].nq - q0), 0});
       tiles.push_back((std::min(l2::kQPerCta, h_frames[f].nq - q0) + l2::kQTile - 1) / l2::kQTile);
       total_tiles += tiles.back();
     }

@@ -72,6 +72,9 @@ struct ABlock {          // one resident query block: up to 1024 queries of one 
   const uint8_t* img;    // expanded smem image (kABytes), written by expand_queries_fp4_kernel
   int32_t frame;
   int32_t q0;
+  int32_t nq;            // queries of this block: 128 x (1, 2, 4 or 8 tiles), less at the end of the frame.  Small stores get
+                         // small blocks, so that (block, keyframe) units outnumber the SMs (run_match in lc_abi.cu)
+  int32_t reserved;
 };
 using tc::CtaWork;
 
@@ -99,15 +102,16 @@ __global__ void __launch_bounds__(kExpandThreads)
   const ABlock ab = blocks[blockIdx.x];
   const QFrame fr = frames[ab.frame];
   const int tile = blockIdx.y;
+  if (tile * kQTile >= ab.nq) return;  // a small block: its last tiles do not exist
   uint8_t* img = img_base + (size_t)blockIdx.x * kABytes + (size_t)tile * kATileBytes;
   for (int idx = threadIdx.x; idx < kQTile * 8; idx += kExpandThreads) {
     const int r = idx >> 3, w = idx & 7, q = ab.q0 + tile * kQTile + r;
-    const uint32_t bits = q < fr.nq ? __ldg(reinterpret_cast<const uint32_t*>(fr.q) + (size_t)q * 8 + w) : 0u;
+    const uint32_t bits = tile * kQTile + r < ab.nq ? __ldg(reinterpret_cast<const uint32_t*>(fr.q) + (size_t)q * 8 + w) : 0u;
     *reinterpret_cast<uint4*>(img + tile_offset(r, w)) = expand_word_fp4(bits);
   }
   if (fill_best && fr.best_packed && threadIdx.x < kQTile) {
     const int q = ab.q0 + tile * kQTile + threadIdx.x;
-    if (q < fr.nq) fr.best_packed[q] = ~0ull;
+    if (tile * kQTile + (int)threadIdx.x < ab.nq) fr.best_packed[q] = ~0ull;
   }
 }
 
@@ -260,7 +264,7 @@ __global__ void __launch_bounds__(kThreads, 1)
   const int slot = cw.slot, n_slots = cw.n_slots;
   const ABlock ab = blocks[cw.ablock];
   const QFrame fr = frames[ab.frame];
-  const int nq_blk = min(kQPerCta, fr.nq - ab.q0);            // queries of this block (> 0 by construction)
+  const int nq_blk = ab.nq;                                   // queries of this block (> 0 by construction)
   const int m_tiles = (nq_blk + kQTile - 1) / kQTile;
 
   if (threadIdx.x == 0) {

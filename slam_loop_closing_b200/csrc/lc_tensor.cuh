@@ -67,6 +67,8 @@ struct ABlock {          // one resident query block: 512 queries of one frame
   const uint8_t* img;    // expanded smem image (kABytes), written by expand_queries_kernel
   int32_t frame;
   int32_t q0;
+  int32_t nq;            // queries of the block (the FP4 path sizes its blocks per launch; this kernel's are always full)
+  int32_t reserved;
 };
 struct CtaWork {         // CTA -> (query block, its share of the keyframes): keyframes k0 + slot, + n_slots, ...
   int32_t ablock;
