@@ -122,3 +122,26 @@ def test_world_one_needs_no_process_group():
     want_res, want_best = c_oracle.loop_check(qs[0], np.concatenate(kfs), [len(k) for k in kfs], fids, curs[0], p)
     np.testing.assert_array_equal(rec[0], want_res)
     np.testing.assert_array_equal(best[0], want_best)
+
+
+@pytest.mark.parametrize("world,F,slots,rows", [(1, 1, 5, 7), (2, 1, 3, 0), (3, 2, 4, 11), (8, 3, 1, 5), (4, 1, 0, 3)])
+def test_merge_torch_equals_numpy_restatement(world, F, slots, rows):
+    """the torch form of the shard merge (what lc_merge_shards_device is checked against on the GPU, and what the gloo run
+    above uses): records re-interleaved to global keyframe order k = slot * world + rank, bests merged by UNSIGNED minimum."""
+    from slam_loop_closing_b200.sharded import merge_torch
+    rng = np.random.default_rng(world * 100 + F * 10 + slots + rows)
+    rec_bytes = F * slots * 16
+    contrib_bytes = (rec_bytes + rows * 8 + 15) & ~15
+    recs = rng.integers(-5, 1000, (world, F, slots, 4)).astype(np.int32)
+    bests = rng.integers(0, 1 << 63, (world, rows), dtype=np.uint64) * np.uint64(2) + rng.integers(0, 2, (world, rows)).astype(np.uint64)
+    if rows:
+        bests[0, 0] = np.iinfo(np.uint64).max          # "nothing compared on this shard" must lose against any real value
+        bests[-1, -1] = np.uint64(1) << np.uint64(63)  # the sign bit alone: larger than every value below 2^63
+    buf = np.zeros((world, contrib_bytes), np.uint8)
+    for r in range(world):
+        buf[r, :rec_bytes] = recs[r].reshape(-1).view(np.uint8)
+        buf[r, rec_bytes:rec_bytes + rows * 8] = bests[r].view(np.uint8)
+    rec, best = merge_torch(torch.from_numpy(buf.reshape(-1)), contrib_bytes, world, F, slots, rows)
+    want = recs.transpose(1, 2, 0, 3).reshape(F, slots * world, 4)
+    np.testing.assert_array_equal(rec.numpy(), want)
+    np.testing.assert_array_equal(best.numpy().view(np.uint64), bests.min(axis=0) if rows else np.zeros(0, np.uint64))
