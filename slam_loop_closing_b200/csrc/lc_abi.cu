@@ -356,6 +356,23 @@ int fill_best(lc_ctx* c, cudaStream_t st, uint64_t* d_best, size_t n) {
   return LC_OK;
 }
 
+// Launch with programmatic stream serialization (lc_mxf4.cuh: pdl_trigger / pdl_wait): the kernel may be scheduled while its
+// predecessor in the stream is still running and waits inside for its completion.
+template <typename... KArgs, typename... Args>
+cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
+}
+
 // Match n_frames query frames against n_kf keyframes (device tables) on `st`.
 // h_frames mirrors d_frames (needed for nq).  max_rows = max n over the keyframes.
 int run_match(lc_ctx* c, cudaStream_t st, const KfEntry* d_kfs, int n_kf, int max_rows, const QFrame* d_frames,
@@ -503,20 +520,18 @@ int run_match(lc_ctx* c, cudaStream_t st, const KfEntry* d_kfs, int n_kf, int ma
             MatchTimer mt(c, st);
             // specialisation of an issue-bound kernel: full-width train tiles only
             auto launch = [&](auto kern) {
-              kern<<<(unsigned)work.size(), fx::kThreads, fx::kSmemAlloc, st>>>(d_kfs, k0, kc, d_frames, (const fx::ABlock*)d_blocks, d_work,
-                                                                               (uint16_t*)c->d_scratch.p, stride, kb);
+              return launch_pdl(kern, dim3((unsigned)work.size()), dim3(fx::kThreads), fx::kSmemAlloc, st, d_kfs, k0, kc, d_frames,
+                                (const fx::ABlock*)d_blocks, (const tc::CtaWork*)d_work, (uint16_t*)c->d_scratch.p, stride, kb);
             };
-            if (full_tiles) launch(fx::mxf4_match_kernel<true>);
-            else launch(fx::mxf4_match_kernel<false>);
+            LC_CUDA(c, full_tiles ? launch(fx::mxf4_match_kernel<true>) : launch(fx::mxf4_match_kernel<false>));
           }
-          LC_CUDA(c, cudaGetLastError());
           const int n_fin = (kc * n_frames + fx::kFinWarps - 1) / fx::kFinWarps;
           if (fused_finish)
-            fx::finish_kernel<<<n_fin + resolve_grid, 256, 0, st>>>(n_fin, d_kfs, n_kf, d_frames, n_frames, (const uint16_t*)c->d_scratch.p, stride,
-                                                                     d_results, kb);
+            LC_CUDA(c, launch_pdl(fx::finish_kernel, dim3(n_fin + resolve_grid), dim3(256), 0, st, n_fin, d_kfs, n_kf, d_frames, n_frames,
+                                  (const uint16_t*)c->d_scratch.p, stride, d_results, kb));
           else
-            fx::finalize_dist_kernel<<<n_fin, fx::kFinWarps * 32, 0, st>>>(d_kfs, n_kf, k0, kc, d_frames, n_frames,
-                                                                           (const uint16_t*)c->d_scratch.p, stride, d_results, kb);
+            LC_CUDA(c, launch_pdl(fx::finalize_dist_kernel, dim3(n_fin), dim3(fx::kFinWarps * 32), 0, st, d_kfs, n_kf, k0, kc, d_frames, n_frames,
+                                  (const uint16_t*)c->d_scratch.p, stride, d_results, kb));
         } else {
           LC_CUDA(c, cudaMemsetAsync(c->d_scratch.p, 0xff, (size_t)kc * n_frames * stride * 4, st));
           {

@@ -93,12 +93,22 @@ __device__ __forceinline__ uint4 expand_word_fp4(uint32_t x) {
 // 16-byte chunk index XOR (row & 7)  (Swizzle<3,4,3>)
 __device__ __forceinline__ uint32_t tile_offset(int r, int w) { return (uint32_t)r * 128u + (((uint32_t)w ^ ((uint32_t)r & 7u)) << 4); }
 
+// ---------------------------------------------------------------- programmatic dependent launch
+// The kernels of a loop check (expand -> match -> finish) are launched with programmatic stream serialization: a kernel may
+// be scheduled as soon as every CTA of its predecessor has called pdl_trigger() (all of them do so at their start), runs
+// the part of its prologue that touches no global memory, and blocks in pdl_wait() until the predecessor grid has completed
+// and its writes are visible.  That takes the launch latency of two kernels out of a small check; with an ordinary launch
+// both calls are no-ops.
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // one launch per loop check, grid (query blocks, 8): every 128-query tile of every (frame, 1024-query block) gets its A
 // image in global memory.  fill_best: the per-query global best of those queries is also put to its idle value here
 // (all ones), which saves the loop check a launch of its own for that.
 constexpr int kExpandThreads = 512;
 __global__ void __launch_bounds__(kExpandThreads)
     expand_queries_fp4_kernel(const ABlock* __restrict__ blocks, const QFrame* __restrict__ frames, uint8_t* img_base, int fill_best) {
+  pdl_trigger();  // (its own inputs were uploaded by copies that completed before this kernel started)
   const ABlock ab = blocks[blockIdx.x];
   const QFrame fr = frames[ab.frame];
   const int tile = blockIdx.y;
@@ -258,6 +268,7 @@ __global__ void __launch_bounds__(kThreads, 1)
   const uint32_t acc_empty = acc_full + 8 * kAccStages;       // [kAccStages] one arrival per epilogue warp
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 1 + 2 * kBStages + 2 * kAccStages);
 
+  pdl_trigger();
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);  // warp-uniform by construction
   const int lane = threadIdx.x & 31;
   const CtaWork cw = work[blockIdx.x];
@@ -292,6 +303,9 @@ __global__ void __launch_bounds__(kThreads, 1)
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  // everything above touched shared and tensor memory only; from here on the query images (expand kernel), the distance
+  // scratch (the previous batch's finalize kernel still reads it) and the per-query bests are in play
+  pdl_wait();
 
   if (warp == kMmaWarp) {
     // ===================== MMA issuer =====================
@@ -521,6 +535,8 @@ __device__ __forceinline__ void finalize_dist_body(int block, const KfEntry* __r
 __global__ void __launch_bounds__(kFinWarps * 32)
     finalize_dist_kernel(const KfEntry* __restrict__ kfs, int n_kf, int k0, int kc, const QFrame* __restrict__ frames, int n_frames,
                          const uint16_t* __restrict__ scratch, int scratch_stride, lc_kf_result* __restrict__ results, Knobs kb) {
+  pdl_trigger();
+  pdl_wait();
   finalize_dist_body(blockIdx.x, kfs, n_kf, k0, kc, frames, n_frames, scratch, scratch_stride, results, kb);
 }
 
@@ -569,6 +585,7 @@ __device__ __forceinline__ void resolve_best_body(int block, int n_blocks, const
 }
 __global__ void __launch_bounds__(256)
     resolve_best_kernel(const KfEntry* __restrict__ kfs, const QFrame* __restrict__ frames, int n_frames) {
+  pdl_wait();
   resolve_best_body(blockIdx.x, gridDim.x, kfs, frames, n_frames);
 }
 // Both steps after the matching kernel in one launch when all keyframes went through in one batch (they are independent:
@@ -577,6 +594,7 @@ static_assert(kFinWarps * 32 == 256, "finish_kernel runs both bodies with 256 th
 __global__ void __launch_bounds__(256)
     finish_kernel(int n_fin, const KfEntry* __restrict__ kfs, int n_kf, const QFrame* __restrict__ frames, int n_frames,
                   const uint16_t* __restrict__ scratch, int scratch_stride, lc_kf_result* __restrict__ results, Knobs kb) {
+  pdl_wait();
   if ((int)blockIdx.x < n_fin)
     finalize_dist_body(blockIdx.x, kfs, n_kf, 0, n_kf, frames, n_frames, scratch, scratch_stride, results, kb);
   else
