@@ -296,6 +296,12 @@ class Context:
         self._ck(self._lib.lc_l2_db_append(self._h, int(frame_id), _ptr(a), len(a), st, ty, C.byref(k)))
         return k.value
 
+    def l2_db_append_meta(self, frame_id, n):
+        """Record a view this shard does not own (only its place in the global order matters)."""
+        k = C.c_int64()
+        self._ck(self._lib.lc_l2_db_append(self._h, int(frame_id), None, int(n), 128, 1, C.byref(k)))
+        return k.value
+
     def l2_db_size(self):
         n, nl = C.c_int64(), C.c_int64()
         self._ck(self._lib.lc_l2_db_size(self._h, C.byref(n), C.byref(nl)))

@@ -185,3 +185,72 @@ class ShardedLoopDB:
         dist.all_gather_into_tensor(gathered, contrib, group=self.group)
         merge = getattr(self.shard, "merge", merge_torch)
         return merge(gathered, contrib_bytes, self.world, F, slots, rows)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# The shipped pipeline's SIFT / L2 loop search (src/main.cpp:1375-1392) over the same partitioning: view k lives on rank
+# k % world; a check is independent per view, so the only exchange is an all_gather of the 16-byte per-view records.
+
+_L2_SENTINEL = (-1, 0, -1, 0)
+
+
+class NativeL2Shard:
+    """This rank's views in an lc_ctx (lc_l2_* entry points)."""
+
+    def __init__(self, rank, world, device, **cfg):
+        self.device = torch.device("cuda", device)
+        self.ctx = _native.Context(device=device, shard_rank=rank, shard_world=world, **cfg)
+
+    def append(self, frame_id, desc, n):
+        if desc is None:
+            self.ctx.l2_db_append_meta(frame_id, n)
+        else:
+            self.ctx.l2_db_append(frame_id, desc)
+
+    def loop_check(self, q, current_frame_id, loop_gap, ratio, min_rows):
+        return self.ctx.l2_loop_check(q, current_frame_id, loop_gap, ratio, min_rows)
+
+
+class ShardedL2DB:
+    """Every rank calls every method with the same arguments (SPMD)."""
+
+    def __init__(self, group=None, device=None, shard=None, **cfg):
+        self.group = group
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        if shard is None:
+            device = device if device is not None else torch.cuda.current_device()
+            shard = NativeL2Shard(self.rank, self.world, device, **cfg)
+        self.shard = shard
+        self.n_views = 0
+
+    def owns(self, k):
+        return k % self.world == self.rank
+
+    def append(self, frame_id, desc, n=None):
+        """desc ((n, 128) SIFT descriptors, u8 or f32) may be None on ranks that do not own this view (then n is required)."""
+        k = self.n_views
+        own = self.owns(k)
+        if own and desc is None:
+            raise ValueError(f"rank {self.rank} owns view {k} but got no descriptors")
+        self.shard.append(frame_id, desc if own else None, len(desc) if desc is not None else int(n))
+        self.n_views += 1
+        return k
+
+    def loop_check(self, q, current_frame_id, loop_gap, ratio=0.7, min_rows=100):
+        """L2_RESULT records of all views in global order: n_good = matches that survive the ratio test, -1 where the
+        pair is skipped (too recent, or fewer than min_rows rows on either side)."""
+        local = np.ascontiguousarray(self.shard.loop_check(q, current_frame_id, loop_gap, ratio, min_rows), _native.L2_RESULT)
+        if self.world == 1:
+            return local
+        slots = (self.n_views + self.world - 1) // self.world
+        dev = getattr(self.shard, "device", None)
+        mine = torch.tensor(_L2_SENTINEL, dtype=torch.int32).repeat(slots, 1)
+        mine[:len(local)] = torch.from_numpy(local.view(np.int32).reshape(-1, 4))
+        if dev is not None:
+            mine = mine.to(dev)
+        gathered = torch.empty((self.world * slots, 4), dtype=torch.int32, device=mine.device)
+        dist.all_gather_into_tensor(gathered, mine, group=self.group)
+        # [world, slots, 4] -> [slots, world, 4]: global view k = slot * world + rank
+        merged = gathered.view(self.world, slots, 4).permute(1, 0, 2).reshape(slots * self.world, 4)[:self.n_views].contiguous()
+        return merged.cpu().numpy().view(_native.L2_RESULT).reshape(-1)

@@ -150,6 +150,33 @@ def test_l2_second_neighbour_inside_and_outside_the_best_rows_group(lc):
             assert (r["second"][~has2] == -1).all()
 
 
+@pytest.mark.parametrize("world", [2, 3])
+def test_l2_sharded_stores_merge_equals_unsharded(lc, world):
+    """view k lives on the context with k % world == rank (lc_config.shard_rank / shard_world, as the Hamming store);
+    the per-view records of the shards, interleaved, are the unsharded check's (ShardedL2DB does this over NCCL)."""
+    from slam_loop_closing_b200.sharded import NativeL2Shard
+    rng = np.random.default_rng(13)
+    q = rng.integers(0, 200, (900, 128)).astype(np.uint8)
+    views = [rng.integers(0, 200, (int(rng.integers(60, 500)), 128)).astype(np.uint8) for _ in range(31)]
+    for k in range(0, 31, 4):
+        m = min(len(views[k]), 250)
+        views[k][:m] = np.clip(q[:m].astype(np.int32) + rng.integers(-2, 3, (m, 128)), 0, 255).astype(np.uint8)
+    with lc.Context() as c0:
+        for k, v in enumerate(views):
+            c0.l2_db_append(k, v)
+        want = c0.l2_loop_check(q, 40, 12, 0.7, 100)
+    merged = np.zeros(len(views), want.dtype)
+    for r in range(world):
+        sh = NativeL2Shard(r, world, 0)
+        for k, v in enumerate(views):
+            sh.append(k, v if k % world == r else None, len(v))
+        assert sh.ctx.l2_db_size() == dict(keyframes=len(views), local_keyframes=len(range(r, len(views), world)))
+        merged[r::world] = sh.loop_check(q, 40, 12, 0.7, 100)
+        sh.ctx.close()
+    np.testing.assert_array_equal(merged, want)
+    assert (want["n_good"][:29:4] > 100).all() and (want["n_good"][29:] == -1).all()
+
+
 def test_l2_rejects_non_sift_values(lc):
     with lc.Context() as c:
         with pytest.raises(lc.LcError):

@@ -145,3 +145,63 @@ def test_merge_torch_equals_numpy_restatement(world, F, slots, rows):
     want = recs.transpose(1, 2, 0, 3).reshape(F, slots * world, 4)
     np.testing.assert_array_equal(rec.numpy(), want)
     np.testing.assert_array_equal(best.numpy().view(np.uint64), bests.min(axis=0) if rows else np.zeros(0, np.uint64))
+
+
+# ---- the SIFT / L2 loop search over the same partitioning (ShardedL2DB): per-view records, all_gather only
+class L2OracleShard:
+    """Test double with NativeL2Shard's interface, computing on the CPU L2 oracle."""
+
+    def __init__(self, rank, world):
+        self.rank, self.world, self.views, self.g = rank, world, [], 0
+
+    def append(self, frame_id, desc, n):
+        if self.g % self.world == self.rank:
+            self.views.append((frame_id, np.asarray(desc)))
+        self.g += 1
+
+    def loop_check(self, q, current_frame_id, loop_gap, ratio, min_rows):
+        from oracle import l2_oracle
+        return l2_oracle.loop_check(q, [v for _, v in self.views], [f for f, _ in self.views], current_frame_id, loop_gap, ratio, min_rows)
+
+
+def _l2_case():
+    rng = np.random.default_rng(9)
+    q = rng.integers(0, 200, (150, 128)).astype(np.uint8)
+    views = []
+    for k in range(11):
+        v = rng.integers(0, 200, (int(rng.integers(5, 200)), 128)).astype(np.uint8)
+        if k % 3 == 0:
+            m = min(len(v), 100)
+            v[:m] = np.clip(q[:m].astype(np.int32) + rng.integers(-2, 3, (m, 128)), 0, 255).astype(np.uint8)
+        views.append(v)
+    return q, views, list(range(0, 22, 2))
+
+
+def _l2_worker(rank, world, port, ret):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from slam_loop_closing_b200.sharded import ShardedL2DB
+        q, views, fids = _l2_case()
+        db = ShardedL2DB(shard=L2OracleShard(rank, world))
+        for k, (fid, v) in enumerate(zip(fids, views)):
+            db.append(fid, v if db.owns(k) else None, n=len(v))
+        res = db.loop_check(q, 24, 6, 0.8, 20)
+        if rank == world - 1:
+            ret["res"] = res
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_sharded_l2_loop_check_equals_unsharded_over_gloo(world):
+    from oracle import l2_oracle
+    q, views, fids = _l2_case()
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_l2_worker, args=(world, _free_port(), ret), nprocs=world, join=True)
+    want = l2_oracle.loop_check(q, views, fids, 24, 6, 0.8, 20)
+    np.testing.assert_array_equal(ret["res"], want)
+    assert (want["n_good"] > 0).any() and (want["n_good"] == -1).any()
