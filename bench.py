@@ -4,8 +4,9 @@
 One "step" = one loop check: a 2000-descriptor query frame against the whole keyframe DB
 (BASELINE config 4: 100k keyframes x 2000 rows = 200 M rows, 6.4 GB), i.e. 400 G descriptor pairs.
 With --gpus N (launched by torchrun, one rank per GPU) the DB is sharded keyframe k -> rank k % N
-(strong scaling: total work fixed), and every step ends with the path's real exchange: an NCCL
-all_reduce(MIN) of the packed per-query best and an all_gather of the per-keyframe records.
+(strong scaling: total work fixed), and every step ends with the path's real exchange: ONE NCCL all_gather of
+every rank's [per-keyframe records | packed per-query bests] and one merge kernel (unsigned min of the bests,
+records re-interleaved into global keyframe order).
 
   value   : whole-job Gpairs/s with the query already resident in HBM (lc_loop_check_batch_device on
             torch's current stream + the collectives), CUDA events, max over ranks.
@@ -49,6 +50,20 @@ WORKLOADS = {
     "c4": dict(keyframes=100_000, name="C4: 2000-descriptor query vs 100k-keyframe DB (200M rows x 256 bit, 6.4 GB)"),
     "c3": dict(keyframes=1_000, name="C3: 2000-descriptor query vs 1k-keyframe DB (2M rows, 64 MB)"),
 }
+
+
+def workload_config(args, world):
+    """The `config` object of the JSON line - the same for both arms (the reference arm times a bounded sample OF this
+    workload and says so in cpu_baseline.sample)."""
+    wl = WORKLOADS[args.workload]
+    n_kf = args.keyframes or wl["keyframes"]
+    local_rows = ((n_kf + world - 1) // world) * ROWS_PER_KF  # rank 0's shard, the largest
+    return {"workload": wl["name"] if not args.keyframes else f"{n_kf}-keyframe DB x {ROWS_PER_KF} rows", "keyframes": n_kf,
+            "rows_per_keyframe": ROWS_PER_KF, "nq": NQ, "pairs_per_step": float(NQ) * ROWS_PER_KF * n_kf,
+            "sharding": f"keyframe k -> rank k % {world}; one NCCL all_gather of [records | packed bests] + one merge kernel per step"
+                        if world > 1 else "single GPU",
+            "kernel": args.kernel,
+            "l2": f"inputs larger than L2: each step streams the {local_rows * 32 / 1e9:.2f} GB DB shard from HBM"}
 
 
 def peaks():
@@ -163,14 +178,14 @@ def run_reference(args):
             times.append(dt)
     tot = float(np.sum(times))
     val = pairs * len(times) / tot / 1e9
-    sample = f"each step = {n} keyframes x {ROWS_PER_KF} rows vs the {NQ}-row query ({pairs / 1e9:.1f} Gpairs); {kind}"
+    sample = (f"each step = a bounded sample of the workload: {n} of its keyframes x {ROWS_PER_KF} rows vs the {NQ}-row query "
+              f"({pairs / 1e9:.1f} Gpairs); {kind}")
     print(json.dumps({
         "impl": "reference", "metric": "Gpairs/s 256-bit Hamming BF match (loop check vs keyframe DB)", "value": val,
         "unit": "Gpairs/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": tot / len(times) * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "u32", "data": "synthetic",
-        "config": {"workload": WORKLOADS[args.workload]["name"] + " - bounded CPU sample of it", "nq": NQ,
-                   "rows_per_keyframe": ROWS_PER_KF, "sample_keyframes": n},
+        "config": workload_config(args, args.gpus),
         "cpu_baseline": {"value": val, "unit": "Gpairs/s", "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": "Gpairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -194,7 +209,8 @@ def build_db(db, torch, n_kf, rank, world, device, plant_at, q_dev):
             chunk[plant_at - c0] = q_dev[perm]
         first = (rank - c0) % world  # first owned keyframe inside the chunk
         mine = chunk[first::world].contiguous()
-        ctx.db_append_many_device(np.arange(c0, c1, dtype=np.int32), np.full(c1 - c0, ROWS_PER_KF, np.int32), mine.data_ptr())
+        ctx.db_append_many_device(np.arange(c0, c1, dtype=np.int32), np.full(c1 - c0, ROWS_PER_KF, np.int32), mine.data_ptr(),
+                                  torch.cuda.current_stream().cuda_stream or 1)  # copies ordered behind the generator kernels
         ctx.synchronize()
         db.n_keyframes += c1 - c0
         del chunk, mine
@@ -368,7 +384,8 @@ def main():
         roof = {
             "bound": "tensor", "achieved": ach, "peak": ratio * bf16, "unit": "TFLOP/s", "frac": ach / (ratio * bf16),
             "traffic": TRAFFIC_BYTES_PER_KF * sizes["local_keyframes"] / match_launches,
-            "kernel": kernel_names[timing.path], "ms_per_launch": m_ms / match_launches, "launches_per_step": match_launches,
+            "kernel": kernel_names[timing.path], "path": "tcgen05 mxf4 GEMM + max, best row resolved afterwards" if timing.path == 4 else "tcgen05 int8 GEMM + arg-max",
+            "ms_per_launch": m_ms / match_launches, "launches_per_step": match_launches,
             "algorithmic_flop_per_launch": pairs_per_gpu * 512 / match_launches,
             "peak_source": f"{'measured' if pk else 'fallback'} cuBLAS bf16 burst {bf16:.1f} TFLOP/s x {ratio:.0f} ({kind} MAC rate / bf16 MAC rate); "
                            f"of {'measured' if pk else 'fallback'}",
@@ -386,7 +403,8 @@ def main():
         ach = pairs_s / 1e9
         roof = {
             "bound": "int_popc", "achieved": ach, "peak": popc_peak, "unit": "Gpairs/s", "frac": ach / popc_peak, "traffic": None,
-            "kernel": kernel_names.get(timing.path, "?"), "ms_per_launch": m_ms / match_launches,
+            "kernel": kernel_names.get(timing.path, "?"), "path": {1: "whole-keyframe scan", 2: "split + finalize"}.get(timing.path, "?"),
+            "ms_per_launch": m_ms / match_launches,
             "note": f"per GPU; integer kernels (neither HBM nor tensor bounds them): peak = {n_sm} SM x {POPC_PER_CLK_PER_SM} POPC/clk x "
                     f"{sm_max:.0f} MHz / {POPC_PER_PAIR} POPC per pair; the carry-save kernel needs 4 POPC per pair, so frac may exceed 1",
             "hbm": hbm,
@@ -396,11 +414,7 @@ def main():
         "value": pairs_per_step * args.steps / (dev_ms * 1e-3) / 1e9, "unit": "Gpairs/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": {4: "fp4", 3: "s8"}.get(timing.path, "u32"), "data": "synthetic",
-        "config": {"workload": wl["name"] if not args.keyframes else f"{n_kf}-keyframe DB x {ROWS_PER_KF} rows", "keyframes": n_kf,
-                   "rows_per_keyframe": ROWS_PER_KF, "nq": NQ, "pairs_per_step": pairs_per_step,
-                   "sharding": f"keyframe k -> rank k % {world}; NCCL all_reduce(MIN) u64 + all_gather per step" if world > 1 else "single GPU",
-                   "kernel": args.kernel, "path": {1: "whole-keyframe scan", 2: "split + finalize", 3: "tcgen05 int8 GEMM + arg-max", 4: "tcgen05 mxf4 GEMM + max, best row resolved afterwards"}.get(timing.path, "?"),
-                   "l2": f"inputs larger than L2: each step streams the {sizes['local_rows'] * 32 / 1e9:.2f} GB DB shard from HBM"},
+        "config": workload_config(args, world),
         "e2e": {"value": pairs_per_step * args.steps / (e2e_ms * 1e-3) / 1e9, "unit": "Gpairs/s", "ms_per_step": e2e_ms / args.steps,
                 "h2d_bytes_per_step": NQ * 32, "d2h_bytes_per_step": int(n_kf * 16 + NQ * 8) if world == 1 else int((n_kf + world) * 16 + NQ * 8),
                 "api": "lc_loop_check (C ABI, host buffers)" if world == 1 else "ShardedLoopDB.loop_check (host buffers, NCCL merge)"},
@@ -503,7 +517,8 @@ def extras(lc, torch, q, kernel):
         g = torch.Generator(device="cuda")
         g.manual_seed(DB_SEED)
         rows = torch.randint(0, 256, (1000 * 2000, 32), dtype=torch.uint8, device="cuda", generator=g)
-        c.db_append_many_device(np.arange(1000, dtype=np.int32), np.full(1000, 2000, np.int32), rows.data_ptr())
+        c.db_append_many_device(np.arange(1000, dtype=np.int32), np.full(1000, 2000, np.int32), rows.data_ptr(),
+                                torch.cuda.current_stream().cuda_stream or 1)
         c.synchronize()
         for _ in range(3):
             c.loop_check(q, 1029)

@@ -31,9 +31,12 @@
 extern "C" {
 #endif
 
-#define LC_ABI_VERSION 1
+#define LC_ABI_VERSION 2 /* 2: lc_db_append_many_device takes the producer stream; LC_MAX_STORE_ROWS; lc_process_frame */
 #define LC_DESC_BYTES 32       /* 256-bit ORB descriptor, README.md:115 */
 #define LC_MAX_ROWS_PER_KF ((1 << 20) - 1) /* rows of one frame; index shares a u32 key with the distance */
+/* rows of ALL keyframes of ALL shards together: best_packed = distance << 32 | global_row keeps the global row id in
+ * 32 bits (137 GB of descriptors).  An append that would cross it fails with LC_ERR_CAPACITY and changes nothing. */
+#define LC_MAX_STORE_ROWS (1ll << 32)
 
 typedef struct lc_ctx lc_ctx;
 
@@ -42,7 +45,7 @@ typedef enum lc_status {
   LC_ERR_INVALID = 1,  /* bad argument */
   LC_ERR_CUDA = 2,     /* CUDA runtime/driver failure (message has the CUDA error string) */
   LC_ERR_NOMEM = 3,    /* host or device allocation failed */
-  LC_ERR_CAPACITY = 4, /* caller-provided output array too small */
+  LC_ERR_CAPACITY = 4, /* caller-provided output array too small, or the store is full (LC_MAX_STORE_ROWS) */
   LC_ERR_IO = 5        /* lc_db_save / lc_db_load */
 } lc_status;
 
@@ -142,10 +145,13 @@ int32_t lc_db_append(lc_ctx* ctx, int32_t frame_id, const uint8_t* desc, int32_t
  * keyframes this shard does not own (or when n_rows[i] == 0). */
 int32_t lc_db_append_many(lc_ctx* ctx, int32_t count, const int32_t* frame_ids, const int32_t* n_rows,
                           const uint8_t* const* desc);
-/* Same with device-resident source rows: d_rows holds the rows of the keyframes of this call that
- * THIS shard owns, back to back (device-to-device copy on the context's stream). */
+/* Same with device-resident source rows: d_rows holds the rows of the keyframes of this call that THIS shard owns, back
+ * to back (device-to-device copies).  `cuda_stream` is the stream whose work produced d_rows (a cudaStream_t;
+ * cudaStreamLegacy (0x1) for the legacy default stream): the copies are ordered behind everything queued on it so far,
+ * and it is made to wait for them, so the caller may reuse or free d_rows in stream order right after the call.  NULL:
+ * the rows are already complete (the caller has synchronised) and must stay untouched until lc_synchronize(). */
 int32_t lc_db_append_many_device(lc_ctx* ctx, int32_t count, const int32_t* frame_ids, const int32_t* n_rows,
-                                 const void* d_rows);
+                                 const void* d_rows, void* cuda_stream);
 /* Global and local (this shard) keyframe / row counts; any pointer may be NULL. */
 int32_t lc_db_size(const lc_ctx* ctx, int64_t* n_keyframes, int64_t* n_rows, int64_t* n_local_keyframes,
                    int64_t* n_local_rows);
@@ -197,8 +203,12 @@ int32_t lc_loop_check(lc_ctx* ctx, const uint8_t* q, int32_t nq, size_t q_stride
                       lc_kf_result* results, int64_t results_cap, int64_t* n_results, uint64_t* best_packed);
 /* The same in two halves, so that the host can run ORB detection of the next frame (or anything else) while the GPU
  * scans the store: _begin copies the query, queues upload + kernels + result download on the context's stream and
- * returns at once; _end waits and hands out what lc_loop_check would have returned (*n_results records).  Between the
- * two no other call on this context is allowed except lc_synchronize / lc_last_error / lc_db_size. */
+ * returns at once; _end waits and hands out what lc_loop_check would have returned (*n_results records).  The pending
+ * check keeps its own pinned result buffer, so between the two every call except another loop check (host-buffer
+ * lc_loop_check*, lc_detect_loops, lc_process_frame) and lc_db_load is allowed - the next frame's lc_match_pair, an
+ * lc_db_append (the pending check does not see the new keyframe), lc_match_keyframes.  Such a call runs on the same
+ * stream BEHIND the check: it returns only after the check has finished on the GPU, so make it before _begin or after
+ * _end when its latency matters; it is not event-timed, and lc_get_last_timing describes the check again after _end. */
 int32_t lc_loop_check_begin(lc_ctx* ctx, const uint8_t* q, int32_t nq, size_t q_stride, int32_t current_frame_id,
                             int32_t want_best);
 int32_t lc_loop_check_end(lc_ctx* ctx, lc_kf_result* results, int64_t results_cap, int64_t* n_results,
@@ -227,8 +237,12 @@ int32_t lc_merge_shards_device(lc_ctx* ctx, const void* d_gathered, int64_t cont
 /* ---- device-pointer variants: everything already in HBM, asynchronous on `cuda_stream`
  *      (a cudaStream_t; NULL = the context's own non-blocking stream - pass cudaStreamLegacy (0x1) to
  *      mean the legacy default stream).  d_q: contiguous 32-byte rows, 16-byte
- *      aligned.  Used for multi-GPU merging (NCCL min all-reduce of d_best_packed, all-gather of
- *      d_results) and for kernel-only timing.  d_best_packed may be NULL. ---- */
+ *      aligned.  Used for multi-GPU merging (all-gather of [d_results | d_best_packed], lc_merge_shards_device)
+ *      and for kernel-only timing.  d_best_packed may be NULL.
+ *      A context's calls share its scratch buffers, so the library serialises them across streams itself: a call
+ *      on `cuda_stream` waits (on the device, by events) for everything the context queued before on any stream,
+ *      and later calls wait for it.  A stream handed in must stay alive until the call returns; the caller still
+ *      synchronises with ITS stream before it reads d_results. ---- */
 int32_t lc_loop_check_device(lc_ctx* ctx, const void* d_q, int32_t nq, int32_t current_frame_id,
                              lc_kf_result* d_results, uint64_t* d_best_packed, void* cuda_stream);
 int32_t lc_loop_check_batch_device(lc_ctx* ctx, int32_t n_frames, const void* d_q, const int32_t* nq,

@@ -21,6 +21,14 @@ def _nvcc():
     raise RuntimeError("nvcc not found: liblc_b200.so cannot be built (there is no CPU fallback)")
 
 
+def have_nvcc():
+    try:
+        _nvcc()
+        return True
+    except RuntimeError:
+        return False
+
+
 def stale():
     if not os.path.exists(LIB):
         return True

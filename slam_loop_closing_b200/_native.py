@@ -57,7 +57,7 @@ SYMBOLS = {
     "lc_set_params": (_i32, [_vp, C.POINTER(Config)]),
     "lc_db_append": (_i32, [_vp, _i32, _vp, _i32, _sz, _pi64]),
     "lc_db_append_many": (_i32, [_vp, _i32, _vp, _vp, _vp]),
-    "lc_db_append_many_device": (_i32, [_vp, _i32, _vp, _vp, _vp]),
+    "lc_db_append_many_device": (_i32, [_vp, _i32, _vp, _vp, _vp, _vp]),
     "lc_db_size": (_i32, [_vp, _pi64, _pi64, _pi64, _pi64]),
     "lc_db_clear": (_i32, [_vp]),
     "lc_db_read": (_i32, [_vp, _i64, _vp, _i32, _pi32, _pi32]),
@@ -100,8 +100,14 @@ def load():
         path = os.environ.get("LC_B200_LIB")  # developer knob: A/B another build of the same ABI
         if not path:
             path = _build.LIB
-            if not os.path.exists(path):
-                path = _build.build()
+            if _build.stale():  # missing, or older than a source / header: never run kernels that do not match the tree
+                if _build.have_nvcc():
+                    path = _build.build()
+                elif not os.path.exists(path):
+                    raise RuntimeError("liblc_b200.so is not built and nvcc is not available (there is no CPU fallback)")
+                else:
+                    import warnings
+                    warnings.warn("liblc_b200.so is older than its sources and nvcc is not available: using the stale library")
         lib = C.CDLL(path)
         for name, (res, args) in SYMBOLS.items():
             fn = getattr(lib, name)  # AttributeError here = the .so does not export the declared ABI
@@ -215,10 +221,13 @@ class Context:
                 ptrs[i] = _ptr(a)
         self._ck(self._lib.lc_db_append_many(self._h, cnt, fids.ctypes.data, ns.ctypes.data, ptrs))
 
-    def db_append_many_device(self, frame_ids, n_rows, d_rows_ptr):
+    def db_append_many_device(self, frame_ids, n_rows, d_rows_ptr, stream=None):
+        """stream: raw handle of the CUDA stream that produced the rows (torch: `torch.cuda.current_stream().cuda_stream
+        or 1` - handle 0 is torch's default stream, which the C ABI names cudaStreamLegacy = 0x1); None = the rows are
+        already complete and stay untouched until synchronize()."""
         fids = np.ascontiguousarray(frame_ids, np.int32)
         ns = np.ascontiguousarray(n_rows, np.int32)
-        self._ck(self._lib.lc_db_append_many_device(self._h, len(fids), fids.ctypes.data, ns.ctypes.data, d_rows_ptr))
+        self._ck(self._lib.lc_db_append_many_device(self._h, len(fids), fids.ctypes.data, ns.ctypes.data, d_rows_ptr, stream))
 
     def db_size(self):
         v = [C.c_int64() for _ in range(4)]

@@ -54,6 +54,11 @@ struct lc_ctx {
   cudaStream_t stream = nullptr;
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
   cudaEvent_t pin_ev[2] = {nullptr, nullptr};
+  // cross-stream ordering of the *_device entry points (StreamScope below): everything a context does shares its scratch
+  // buffers, so work on a caller's stream is chained behind the context's own stream and the other way round
+  cudaEvent_t own_ev = nullptr, foreign_ev = nullptr;
+  bool foreign_pending = false;
+  bool pair_state_dirty = false;  // a CUDA failure may have left the pair kernel's keys / ticket state off their idle values
   std::string err;
 
   // ---- store
@@ -86,6 +91,10 @@ struct lc_ctx {
     bool active = false, queued = false;
     size_t res_bytes = 0, best_bytes = 0;
     int64_t n_res = 0, rows = 0;
+    // another call (a pair match, an append) ran between _begin and _end: it ran untimed and the check's timing state
+    // waits here for lc_loop_check_end
+    bool stashed = false, stashed_on = false;
+    lc_timing stashed_timing{};
   } pending;
   bool smem_attr_set = false;  // the tensor kernels' dynamic shared-memory limit has been raised on this device
   // ---- the SIFT / L2 store of the shipped pipeline's matcher (lc_l2.cuh): 128-byte rows + their squared norms
@@ -120,6 +129,7 @@ int fail(lc_ctx* c, int code, const char* fmt, ...) {
   vsnprintf(buf, sizeof buf, fmt, ap);
   va_end(ap);
   if (c) c->err = buf; else g_create_error = buf;
+  if (c && code == LC_ERR_CUDA) c->pair_state_dirty = true;  // pair_device_impl re-initialises keys[] and the ticket state
   return code;
 }
 
@@ -136,6 +146,39 @@ int fail(lc_ctx* c, int code, const char* fmt, ...) {
     int rc_ = (expr);         \
     if (rc_ != LC_OK) return rc_; \
   } while (0)
+
+// Every entry point that takes a `cuda_stream` runs inside one of these.  The context's scratch (pair keys, distance
+// scratch, query images, CTA tables, frame table) is shared by all its calls, so a call on a caller's stream first waits
+// for what the context's own stream has queued, and whoever comes next - on any stream - waits for that call's end.  The
+// events are recorded while the caller's stream is certainly alive (inside its own call).
+struct StreamScope {
+  lc_ctx* c;
+  cudaStream_t st;
+  StreamScope(lc_ctx* ctx, void* cuda_stream) : c(ctx), st(cuda_stream ? (cudaStream_t)cuda_stream : ctx->stream) {}
+  int enter() {
+    if (st != c->stream) {
+      LC_CUDA(c, cudaEventRecord(c->own_ev, c->stream));
+      LC_CUDA(c, cudaStreamWaitEvent(st, c->own_ev, 0));
+    }
+    if (c->foreign_pending) {
+      LC_CUDA(c, cudaStreamWaitEvent(st, c->foreign_ev, 0));
+      c->foreign_pending = false;
+    }
+    return LC_OK;
+  }
+  ~StreamScope() {
+    if (st != c->stream && cudaEventRecord(c->foreign_ev, st) == cudaSuccess) c->foreign_pending = true;
+  }
+};
+// host-buffer calls run on the context's own stream: wait for the last *_device call on a caller's stream, if any
+int enter_host(lc_ctx* c) {
+  LC_CUDA(c, cudaSetDevice(c->cfg.device));
+  if (c->foreign_pending) {
+    LC_CUDA(c, cudaStreamWaitEvent(c->stream, c->foreign_ev, 0));
+    c->foreign_pending = false;
+  }
+  return LC_OK;
+}
 
 int ensure(lc_ctx* c, DevBuf& b, size_t bytes) {
   if (bytes <= b.cap) return LC_OK;
@@ -257,6 +300,10 @@ int upload_rows(lc_ctx* c, uint8_t* dst, const uint8_t* src, int64_t n, size_t s
 int store_append(lc_ctx* c, int32_t frame_id, const uint8_t* desc, int32_t n, size_t stride, bool device_src,
                  int64_t* kf_index) {
   if (n < 0 || n > LC_MAX_ROWS_PER_KF) return fail(c, LC_ERR_INVALID, "n = %d outside [0, %d]", n, LC_MAX_ROWS_PER_KF);
+  // best_packed = distance << 32 | global_row: the store (ALL shards together) ends at LC_MAX_STORE_ROWS rows
+  if (c->g_rows + n > LC_MAX_STORE_ROWS)
+    return fail(c, LC_ERR_CAPACITY, "the store holds %lld rows and cannot take %d more: global row ids are 32 bits (LC_MAX_STORE_ROWS)",
+                (long long)c->g_rows, n);
   const int64_t k = c->g_kf;
   const bool own = (k % c->cfg.shard_world) == c->cfg.shard_rank;
   if (own) {
@@ -664,14 +711,18 @@ int loop_check_device_impl(lc_ctx* c, cudaStream_t st, int n_frames, const void*
 int pair_device_impl(lc_ctx* c, cudaStream_t st, const void* d_q, int nq, const KfEntry& train, const PairOut& po) {
   const int nt = train.n;
   // keys[nq] and {ticket counter, smallest distance} rest at 0xffffffff / {0, 0xffffffff} between calls (the kernel's last CTA puts them back)
+  // A CUDA failure anywhere on the context (an aborted launch, a failed copy) may have left them dirty: both are put back
+  // before the next launch, or every later pair match on this context would be silently wrong.
   const size_t need = (size_t)nq * 4;
-  if (c->d_pairkeys.cap < need) {
+  const bool dirty = c->pair_state_dirty;
+  c->pair_state_dirty = false;
+  if (c->d_pairkeys.cap < need || dirty) {
     LC_TRY(ensure(c, c->d_pairkeys, need));
     LC_CUDA(c, cudaMemsetAsync(c->d_pairkeys.p, 0xff, c->d_pairkeys.cap, st));
   }
-  if (!c->d_paircnt.p) {
+  if (!c->d_paircnt.p || dirty) {
     LC_TRY(ensure(c, c->d_paircnt, 256));
-    const unsigned int idle[2] = {0u, 0xffffffffu};  // ticket counter, smallest distance
+    static const unsigned int idle[2] = {0u, 0xffffffffu};  // ticket counter, smallest distance
     LC_CUDA(c, cudaMemcpyAsync(c->d_paircnt.p, idle, sizeof idle, cudaMemcpyHostToDevice, st));
   }
   // The launch is a whole number of waves of near-equal CTAs, two per SM: the integer pipes bound the kernel, so an SM
@@ -738,6 +789,18 @@ int stage_pair(lc_ctx* c, const uint8_t* q, int64_t nq, size_t qs, const uint8_t
 
 // events = false: the call's path and launch count are still reported, its times read 0
 void timing_begin(lc_ctx* c, bool events = true) {
+  if (c->pending.active && c->pending.queued) {
+    // a call between lc_loop_check_begin and _end: the pending check owns the events, so this call is not timed (its
+    // path and launch count are still reported until _end puts the check's timing back)
+    if (!c->pending.stashed) {
+      c->pending.stashed = true;
+      c->pending.stashed_on = c->timing_on;
+      c->pending.stashed_timing = c->timing;
+    }
+    c->timing = lc_timing{};
+    c->timing_on = false;
+    return;
+  }
   c->timing = lc_timing{};
   c->match_ev_used = 0;
   c->timing_on = events;
@@ -871,6 +934,8 @@ LC_API void lc_destroy(lc_ctx* c) {
   if (c->pin_loop) cudaFreeHost(c->pin_loop);
   for (auto& e : c->ev) if (e) cudaEventDestroy(e);
   for (auto& e : c->pin_ev) if (e) cudaEventDestroy(e);
+  if (c->own_ev) cudaEventDestroy(c->own_ev);
+  if (c->foreign_ev) cudaEventDestroy(c->foreign_ev);
   for (auto& e : c->match_ev) if (e) cudaEventDestroy(e);
   if (c->stream) cudaStreamDestroy(c->stream);
   delete c;
@@ -916,6 +981,8 @@ LC_API int32_t lc_create(const lc_config* cfg, lc_ctx** out) {
     if ((e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming)) != cudaSuccess) return bail("cudaEventCreate", e);
     cudaEventRecord(ev, c->stream);
   }
+  if ((e = cudaEventCreateWithFlags(&c->own_ev, cudaEventDisableTiming)) != cudaSuccess) return bail("cudaEventCreate", e);
+  if ((e = cudaEventCreateWithFlags(&c->foreign_ev, cudaEventDisableTiming)) != cudaSuccess) return bail("cudaEventCreate", e);
   if ((e = cudaMallocHost((void**)&c->pin_up, 2 * kPinHalfBytes)) != cudaSuccess) return bail("cudaMallocHost", e);
   *out = c;
   return LC_OK;
@@ -944,7 +1011,7 @@ LC_API int32_t lc_set_params(lc_ctx* c, const lc_config* g) {
 LC_API int32_t lc_db_append(lc_ctx* c, int32_t frame_id, const uint8_t* desc, int32_t n, size_t stride, int64_t* kf_index) {
   if (!c) return LC_ERR_INVALID;
   LC_GUARD_BEGIN
-  LC_CUDA(c, cudaSetDevice(c->cfg.device));
+  LC_TRY(enter_host(c));
   return store_append(c, frame_id, desc, n, stride, false, kf_index);
   LC_GUARD_END(c)
 }
@@ -953,25 +1020,38 @@ LC_API int32_t lc_db_append_many(lc_ctx* c, int32_t count, const int32_t* frame_
   if (!c) return LC_ERR_INVALID;
   if (count < 0 || (count > 0 && (!frame_ids || !n_rows || !desc))) return fail(c, LC_ERR_INVALID, "bad arguments");
   LC_GUARD_BEGIN
-  LC_CUDA(c, cudaSetDevice(c->cfg.device));
+  LC_TRY(enter_host(c));
   for (int32_t i = 0; i < count; ++i) LC_TRY(store_append(c, frame_ids[i], desc[i], n_rows[i], LC_DESC_BYTES, false, nullptr));
   return LC_OK;
   LC_GUARD_END(c)
 }
 
-// device-resident source rows: d_rows holds the rows of the OWNED keyframes of this call, back to back
-LC_API int32_t lc_db_append_many_device(lc_ctx* c, int32_t count, const int32_t* frame_ids, const int32_t* n_rows, const void* d_rows) {
+// device-resident source rows: d_rows holds the rows of the OWNED keyframes of this call, back to back.  The copies
+// run on the context's own stream (the store's order) behind an event recorded on `cuda_stream`, the stream that
+// produced d_rows; that stream in turn waits for the copies, so stream-ordered reuse of d_rows is safe.
+LC_API int32_t lc_db_append_many_device(lc_ctx* c, int32_t count, const int32_t* frame_ids, const int32_t* n_rows, const void* d_rows,
+                                        void* cuda_stream) {
   if (!c) return LC_ERR_INVALID;
   if (count < 0 || (count > 0 && (!frame_ids || !n_rows))) return fail(c, LC_ERR_INVALID, "bad arguments");
   LC_GUARD_BEGIN
-  LC_CUDA(c, cudaSetDevice(c->cfg.device));
+  LC_TRY(enter_host(c));
+  cudaStream_t producer = (cudaStream_t)cuda_stream;
+  if (producer && producer != c->stream) {
+    LC_CUDA(c, cudaEventRecord(c->foreign_ev, producer));
+    LC_CUDA(c, cudaStreamWaitEvent(c->stream, c->foreign_ev, 0));
+  }
   const uint8_t* p = (const uint8_t*)d_rows;
-  for (int32_t i = 0; i < count; ++i) {
+  int rc = LC_OK;
+  for (int32_t i = 0; i < count && rc == LC_OK; ++i) {
     const bool own = (c->g_kf % c->cfg.shard_world) == c->cfg.shard_rank;
-    LC_TRY(store_append(c, frame_ids[i], own ? p : nullptr, n_rows[i], LC_DESC_BYTES, true, nullptr));
+    rc = store_append(c, frame_ids[i], own ? p : nullptr, n_rows[i], LC_DESC_BYTES, true, nullptr);
     if (own) p += (size_t)n_rows[i] * LC_DESC_BYTES;
   }
-  return LC_OK;
+  if (producer && producer != c->stream) {  // also after a partial failure: some copies may be queued
+    LC_CUDA(c, cudaEventRecord(c->own_ev, c->stream));
+    LC_CUDA(c, cudaStreamWaitEvent(producer, c->own_ev, 0));
+  }
+  return rc;
   LC_GUARD_END(c)
 }
 
@@ -987,7 +1067,7 @@ LC_API int32_t lc_db_size(const lc_ctx* c, int64_t* n_kf, int64_t* n_rows, int64
 LC_API int32_t lc_db_clear(lc_ctx* c) {
   if (!c) return LC_ERR_INVALID;
   LC_GUARD_BEGIN
-  LC_CUDA(c, cudaSetDevice(c->cfg.device));
+  LC_TRY(enter_host(c));
   LC_CUDA(c, cudaStreamSynchronize(c->stream));
   for (void* p : c->slabs) cudaFree(p);
   c->slabs.clear();
@@ -1012,7 +1092,7 @@ static int find_local(lc_ctx* c, int64_t kf_index, size_t* slot) {
 LC_API int32_t lc_db_read(lc_ctx* c, int64_t kf_index, uint8_t* desc_out, int32_t cap_rows, int32_t* n, int32_t* frame_id) {
   if (!c) return LC_ERR_INVALID;
   LC_GUARD_BEGIN
-  LC_CUDA(c, cudaSetDevice(c->cfg.device));
+  LC_TRY(enter_host(c));
   size_t s;
   LC_TRY(find_local(c, kf_index, &s));
   const KfEntry& e = c->h_kf[s];
@@ -1034,7 +1114,7 @@ LC_API int32_t lc_db_read(lc_ctx* c, int64_t kf_index, uint8_t* desc_out, int32_
 LC_API int32_t lc_db_save(lc_ctx* c, const char* path) {
   if (!c || !path) return LC_ERR_INVALID;
   LC_GUARD_BEGIN
-  LC_CUDA(c, cudaSetDevice(c->cfg.device));
+  LC_TRY(enter_host(c));
   LC_CUDA(c, cudaStreamSynchronize(c->stream));
   FILE* f = fopen(path, "wb");
   if (!f) return fail(c, LC_ERR_IO, "cannot open %s for writing", path);
@@ -1071,9 +1151,13 @@ LC_API int32_t lc_db_save(lc_ctx* c, const char* path) {
 LC_API int32_t lc_db_load(lc_ctx* c, const char* path) {
   if (!c || !path) return LC_ERR_INVALID;
   LC_GUARD_BEGIN
-  LC_CUDA(c, cudaSetDevice(c->cfg.device));
-  if (c->g_kf != 0) return fail(c, LC_ERR_INVALID, "lc_db_load needs an empty store (call lc_db_clear)");
-  FILE* f = fopen(path, "rb");
+  LC_TRY(enter_host(c));
+  if (c->g_kf != 0 || !c->h_kf.empty()) return fail(c, LC_ERR_INVALID, "lc_db_load needs an empty store (call lc_db_clear)");
+  struct File {  // closed on every path out, exceptions included
+    FILE* f;
+    ~File() { if (f) fclose(f); }
+  } file{fopen(path, "rb")};
+  FILE* f = file.f;
   if (!f) return fail(c, LC_ERR_IO, "cannot open %s", path);
   bool ok = true;
   auto R = [&](void* p, size_t n) { ok = ok && fread(p, 1, n, f) == n; };
@@ -1083,45 +1167,70 @@ LC_API int32_t lc_db_load(lc_ctx* c, const char* path) {
   R(magic, 8);
   R(hdr, sizeof hdr);
   R(cnt, sizeof cnt);
-  if (!ok || memcmp(magic, "LCB200DB", 8) != 0 || hdr[0] != 1u) {
-    fclose(f);
-    return fail(c, LC_ERR_IO, "%s is not a liblc_b200 store file", path);
-  }
-  if ((int32_t)hdr[1] != c->cfg.shard_rank || (int32_t)hdr[2] != c->cfg.shard_world) {
-    fclose(f);
+  if (!ok || memcmp(magic, "LCB200DB", 8) != 0 || hdr[0] != 1u) return fail(c, LC_ERR_IO, "%s is not a liblc_b200 store file", path);
+  const int64_t rank = c->cfg.shard_rank, world = c->cfg.shard_world;
+  if ((int64_t)hdr[1] != rank || (int64_t)hdr[2] != world)
     return fail(c, LC_ERR_INVALID, "%s holds shard %u/%u, context is %d/%d", path, hdr[1], hdr[2], c->cfg.shard_rank, c->cfg.shard_world);
-  }
+  // The header is not trusted: the counts must describe exactly this shard's slice of a store of g_kf keyframes
+  // (keyframe k on rank k % world, local slot k / world - what find_local and the loop check's records rely on).
+  const int64_t g_kf = cnt[0], g_rows = cnt[1], n_local = cnt[2];
+  if (g_kf < 0 || g_rows < 0 || g_rows > LC_MAX_STORE_ROWS || n_local < 0 || n_local != (g_kf > rank ? (g_kf - rank + world - 1) / world : 0))
+    return fail(c, LC_ERR_IO, "%s: header counts are inconsistent (%lld keyframes, %lld rows, %lld local on shard %lld/%lld)", path,
+                (long long)g_kf, (long long)g_rows, (long long)n_local, (long long)rank, (long long)world);
   struct Rec { int64_t gi, off; int32_t fid, n; };
-  std::vector<Rec> recs((size_t)cnt[2]);
-  for (auto& r : recs) {
+  {  // the table must fit the file: a corrupt count must not become a huge allocation
+    const long pos = ftell(f);
+    if (pos < 0 || fseek(f, 0, SEEK_END) != 0) return fail(c, LC_ERR_IO, "%s: cannot seek", path);
+    const long end = ftell(f);
+    if (end < 0 || fseek(f, pos, SEEK_SET) != 0) return fail(c, LC_ERR_IO, "%s: cannot seek", path);
+    if ((uint64_t)n_local > (uint64_t)(end - pos) / 24u) return fail(c, LC_ERR_IO, "%s is truncated or corrupt (keyframe table)", path);
+  }
+  std::vector<Rec> recs((size_t)n_local);
+  int64_t local_rows = 0, prev_end = 0;
+  for (size_t i = 0; i < recs.size() && ok; ++i) {
+    Rec& r = recs[i];
     R(&r.gi, 16);
     R(&r.fid, 8);
+    if (!ok) break;
+    // global index = slot * world + rank; 0 <= n <= LC_MAX_ROWS_PER_KF; the global row ranges ascend without overlap
+    if (r.gi != (int64_t)i * world + rank || r.n < 0 || r.n > LC_MAX_ROWS_PER_KF || r.off < prev_end || r.off > g_rows - r.n)
+      return fail(c, LC_ERR_IO, "%s: keyframe table entry %zu is corrupt (global index %lld, row offset %lld, %d rows)", path, i,
+                  (long long)r.gi, (long long)r.off, r.n);
+    prev_end = r.off + r.n;
+    local_rows += r.n;
   }
+  if (!ok) return fail(c, LC_ERR_IO, "%s is truncated or corrupt (keyframe table)", path);
+  if (world == 1 && (local_rows != g_rows || (n_local > 0 && recs[0].off != 0)))
+    return fail(c, LC_ERR_IO, "%s: row counts are inconsistent (%lld rows in the table, %lld in the header)", path, (long long)local_rows, (long long)g_rows);
+  // from here on the store is being filled: every failure empties it again
+  int rc = LC_OK;
   std::vector<uint8_t> buf;
-  for (size_t i = 0; i < recs.size() && ok; ++i) {
+  for (size_t i = 0; i < recs.size() && ok && rc == LC_OK; ++i) {
     const Rec& r = recs[i];
-    if (r.n < 0 || r.n > LC_MAX_ROWS_PER_KF) { ok = false; break; }
     buf.resize((size_t)r.n * LC_DESC_BYTES);
     if (r.n) R(buf.data(), buf.size());
     if (!ok) break;
     uint4* rows = nullptr;
-    int rc = slab_alloc(c, r.n, &rows);
+    rc = slab_alloc(c, r.n, &rows);
     if (rc == LC_OK && r.n) rc = upload_rows(c, (uint8_t*)rows, buf.data(), r.n, LC_DESC_BYTES);
-    if (rc != LC_OK) { fclose(f); return rc; }
+    if (rc != LC_OK) break;
     c->h_kf.push_back(KfEntry{rows, r.n, r.fid, r.off});
     c->h_kf_global.push_back(r.gi);
     c->l_rows += r.n;
     c->max_n_local = std::max(c->max_n_local, r.n);
     c->n_partial_kf += (r.n > 0 && !fx::full_tiles_only(r.n)) ? 1 : 0;
   }
-  fclose(f);
-  if (!ok) {
+  if (ok && rc == LC_OK && fgetc(f) != EOF) ok = false;  // trailing bytes: not a file lc_db_save wrote
+  if (rc == LC_OK && ok && cudaStreamSynchronize(c->stream) != cudaSuccess) rc = fail(c, LC_ERR_CUDA, "upload failed while loading %s", path);
+  if (!ok || rc != LC_OK) {
+    const std::string why = c->err;
     lc_db_clear(c);
-    return fail(c, LC_ERR_IO, "%s is truncated or corrupt", path);
+    if (!ok) return fail(c, LC_ERR_IO, "%s is truncated or corrupt (descriptor rows)", path);
+    c->err = why;
+    return rc;
   }
-  c->g_kf = cnt[0];
-  c->g_rows = cnt[1];
-  LC_CUDA(c, cudaStreamSynchronize(c->stream));
+  c->g_kf = g_kf;
+  c->g_rows = g_rows;
   return LC_OK;
   LC_GUARD_END(c)
 }
@@ -1137,7 +1246,7 @@ LC_API int32_t lc_match_pair(lc_ctx* c, const uint8_t* q, int32_t nq, size_t qs,
     empty_pair(n_matches, min_dist, n_good);
     return LC_OK;
   }
-  LC_CUDA(c, cudaSetDevice(c->cfg.device));
+  LC_TRY(enter_host(c));
   timing_begin(c, pair_events(c));
   const uint4* d_t = nullptr;
   LC_TRY(stage_pair(c, q, nq, qs, t, nt, ts, &d_t));
@@ -1158,7 +1267,7 @@ LC_API int32_t lc_match_vs_keyframe(lc_ctx* c, const uint8_t* q, int32_t nq, siz
     empty_pair(n_matches, min_dist, n_good);
     return LC_OK;
   }
-  LC_CUDA(c, cudaSetDevice(c->cfg.device));
+  LC_TRY(enter_host(c));
   timing_begin(c, pair_events(c));
   LC_TRY(stage_query(c, c->d_q, q, nq, qs));
   return pair_host_impl(c, nq, train, train_idx, dist, good, n_matches, min_dist, n_good);
@@ -1172,7 +1281,9 @@ LC_API int32_t lc_match_pair_device(lc_ctx* c, const void* d_q, int32_t nq, cons
   if (nq < 0 || nt < 0 || nq > LC_MAX_ROWS_PER_KF || nt > LC_MAX_ROWS_PER_KF) return fail(c, LC_ERR_INVALID, "row count out of range");
   if (((uintptr_t)d_q | (uintptr_t)d_t) % 16 != 0) return fail(c, LC_ERR_INVALID, "device rows must be 16-byte aligned");
   LC_CUDA(c, cudaSetDevice(c->cfg.device));
-  cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : c->stream;
+  StreamScope scope(c, cuda_stream);
+  LC_TRY(scope.enter());
+  cudaStream_t st = scope.st;
   c->timing_on = false;  // asynchronous entry point: nothing is timed
   if (nq == 0 || nt == 0) {
     if (d_summary) {
@@ -1200,7 +1311,7 @@ LC_API int32_t lc_match_keyframes(lc_ctx* c, const uint8_t* q, int32_t nq, size_
   }
   offsets[0] = 0;
   if (n_sel == 0) return LC_OK;
-  LC_CUDA(c, cudaSetDevice(c->cfg.device));
+  LC_TRY(enter_host(c));
   timing_begin(c);
   LC_TRY(stage_query(c, c->d_q, q, nq, qs));
   // per keyframe on the device: idx[nq] dist[nq] summary[2] good[nq], slices 16-byte aligned
@@ -1208,7 +1319,7 @@ LC_API int32_t lc_match_keyframes(lc_ctx* c, const uint8_t* q, int32_t nq, size_
   const size_t slice = (off_good + (size_t)nq + 15) & ~size_t(15);
   LC_TRY(ensure(c, c->d_out, slice * (size_t)n_sel));
   LC_TRY(ensure_pin_down(c, slice * (size_t)n_sel));
-  LC_CUDA(c, cudaEventRecord(c->ev[1], c->stream));
+  if (c->timing_on) LC_CUDA(c, cudaEventRecord(c->ev[1], c->stream));
   for (int32_t i = 0; i < n_sel; ++i) {
     uint8_t* d = (uint8_t*)c->d_out.p + slice * (size_t)i;
     if (nq == 0 || sel[i].n == 0) {  // cv::BFMatcher returns no matches when either side is empty
@@ -1218,7 +1329,7 @@ LC_API int32_t lc_match_keyframes(lc_ctx* c, const uint8_t* q, int32_t nq, size_
     }
     LC_TRY(pair_device_impl(c, c->stream, c->d_q.p, nq, sel[i], PairOut{(int32_t*)d, (int32_t*)(d + off_dist), d + off_good, (int32_t*)(d + off_sum)}));
   }
-  LC_CUDA(c, cudaEventRecord(c->ev[2], c->stream));
+  if (c->timing_on) LC_CUDA(c, cudaEventRecord(c->ev[2], c->stream));
   LC_CUDA(c, cudaMemcpyAsync(c->pin_down, c->d_out.p, slice * (size_t)n_sel, cudaMemcpyDeviceToHost, c->stream));
   LC_TRY(timing_end(c));
   int64_t total = 0;
@@ -1251,7 +1362,9 @@ LC_API int32_t lc_loop_check_batch_device(lc_ctx* c, int32_t n_frames, const voi
   if (n_frames < 0 || (n_frames > 0 && (!nq || !cur_ids))) return fail(c, LC_ERR_INVALID, "bad arguments");
   if (!d_results && !c->h_kf.empty() && n_frames > 0) return fail(c, LC_ERR_INVALID, "d_results is NULL");
   LC_CUDA(c, cudaSetDevice(c->cfg.device));
-  cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : c->stream;
+  StreamScope scope(c, cuda_stream);
+  LC_TRY(scope.enter());
+  cudaStream_t st = scope.st;
   c->timing_on = false;  // asynchronous entry point: nothing is timed
   return loop_check_device_impl(c, st, n_frames, d_q, nq, cur_ids, d_results, d_best);
   LC_GUARD_END(c)
@@ -1270,7 +1383,9 @@ LC_API int32_t lc_merge_shards_device(lc_ctx* c, const void* d_gathered, int64_t
   if (((uintptr_t)d_gathered | (uintptr_t)d_records_out) % 16 != 0) return fail(c, LC_ERR_INVALID, "lc_merge_shards_device: buffers must be 16-byte aligned");
   if (n_rec * world + rows == 0) return LC_OK;
   LC_CUDA(c, cudaSetDevice(c->cfg.device));
-  cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : c->stream;
+  StreamScope scope(c, cuda_stream);
+  LC_TRY(scope.enter());
+  cudaStream_t st = scope.st;
   const long long items = std::max<long long>(n_rec * world, rows);
   const int grid = (int)std::min<long long>((items + 255) / 256, 8ll * c->num_sms);
   merge_shards_kernel<<<grid, 256, 0, st>>>((const uint8_t*)d_gathered, (size_t)contrib_bytes, world, n_rec, rows, (uint4*)d_records_out, d_best_out);
@@ -1301,7 +1416,7 @@ int loop_check_enqueue_impl(lc_ctx* c, int32_t n_frames, const uint8_t* const* q
   c->pending.n_res = n_kf * n_frames;
   c->pending.rows = rows;
   if (n_frames == 0) return LC_OK;
-  LC_CUDA(c, cudaSetDevice(c->cfg.device));
+  LC_TRY(enter_host(c));
   timing_begin(c, loop_events(c, rows));
   // device side: [query rows | frame table] in d_q, [per-keyframe records | per-query bests] in d_results - one copy in
   // and one copy out when the rows fit the pinned upload buffer (a small check is a chain of latencies, not bandwidth)
@@ -1359,8 +1474,12 @@ int loop_check_collect(lc_ctx* c, lc_kf_result* results, int64_t results_cap, ui
   if (!c->pending.active) return fail(c, LC_ERR_INVALID, "no loop check is pending");
   const lc_ctx::Pending p = c->pending;
   c->pending.active = false;
+  if (p.stashed) {
+    c->timing = p.stashed_timing;
+    c->timing_on = p.stashed_on;
+  }
   if (p.queued) {
-    LC_CUDA(c, cudaSetDevice(c->cfg.device));
+    LC_TRY(enter_host(c));
     LC_TRY(timing_end(c, true, false));
   }
   if (p.n_res > 0 && (!results || results_cap < p.n_res))
@@ -1553,7 +1672,7 @@ int l2_run(lc_ctx* c, const l2::L2Kf* d_kfs, int n_kf, const l2::L2Frame* d_fram
 LC_API int32_t lc_l2_db_append(lc_ctx* c, int32_t frame_id, const void* desc, int32_t n, size_t stride, int32_t type, int64_t* kf_index) {
   if (!c) return LC_ERR_INVALID;
   LC_GUARD_BEGIN
-  LC_CUDA(c, cudaSetDevice(c->cfg.device));
+  LC_TRY(enter_host(c));
   auto& S = c->l2s;
   const int64_t k = S.g_kf;
   const bool own = (k % c->cfg.shard_world) == c->cfg.shard_rank;
@@ -1598,7 +1717,7 @@ LC_API int32_t lc_l2_db_size(const lc_ctx* c, int64_t* n_kf, int64_t* n_local) {
 LC_API int32_t lc_l2_db_clear(lc_ctx* c) {
   if (!c) return LC_ERR_INVALID;
   LC_GUARD_BEGIN
-  LC_CUDA(c, cudaSetDevice(c->cfg.device));
+  LC_TRY(enter_host(c));
   LC_CUDA(c, cudaStreamSynchronize(c->stream));
   for (void* p : c->l2s.slabs) cudaFree(p);
   c->l2s = lc_ctx::L2Store{};
@@ -1624,7 +1743,7 @@ LC_API int32_t lc_l2_match_pair(lc_ctx* c, const void* q, int32_t nq, size_t qs,
     }
     return LC_OK;
   }
-  LC_CUDA(c, cudaSetDevice(c->cfg.device));
+  LC_TRY(enter_host(c));
   timing_begin(c);
   const size_t tn_off = ((size_t)nq * 4 + 255) & ~size_t(255);  // d_l2norm: query norms, then train norms
   LC_TRY(ensure(c, c->d_l2norm, tn_off + (size_t)nt * 4));     // grow once: the two stagings below must not reallocate it
@@ -1643,11 +1762,11 @@ LC_API int32_t lc_l2_match_pair(lc_ctx* c, const void* q, int32_t nq, size_t qs,
   h.fr = l2::L2Frame{(const uint4*)c->d_l2q.p, (const uint32_t*)c->d_l2norm.p, nq, 0, (int32_t*)d, (int32_t*)(d + o_d1), (int32_t*)(d + o_d2), d + o_good};
   LC_TRY(ensure(c, c->d_l2frames, sizeof h));
   LC_CUDA(c, cudaMemcpyAsync(c->d_l2frames.p, &h, sizeof h, cudaMemcpyHostToDevice, c->stream));
-  LC_CUDA(c, cudaEventRecord(c->ev[1], c->stream));
+  if (c->timing_on) LC_CUDA(c, cudaEventRecord(c->ev[1], c->stream));
   const l2::L2Kf* d_kf = (const l2::L2Kf*)c->d_l2frames.p;
   const l2::L2Frame* d_fr = (const l2::L2Frame*)((const uint8_t*)c->d_l2frames.p + offsetof(decltype(h), fr));
   LC_TRY(l2_run(c, d_kf, 1, d_fr, &h.fr, 1, (l2::L2Result*)(d + o_res), l2::L2Knobs{-(1 << 30), 0, ratio}));
-  LC_CUDA(c, cudaEventRecord(c->ev[2], c->stream));
+  if (c->timing_on) LC_CUDA(c, cudaEventRecord(c->ev[2], c->stream));
   LC_CUDA(c, cudaMemcpyAsync(c->pin_down, d, bytes, cudaMemcpyDeviceToHost, c->stream));
   LC_TRY(timing_end(c));
   const uint8_t* hp = c->pin_down;
@@ -1674,7 +1793,7 @@ LC_API int32_t lc_l2_loop_check(lc_ctx* c, const void* q, int32_t nq, size_t qs,
   if (n_results) *n_results = n_kf;
   if (n_kf > 0 && (!results || cap < n_kf)) return fail(c, LC_ERR_CAPACITY, "results_cap %lld < %lld", (long long)cap, (long long)n_kf);
   if (n_kf == 0) return LC_OK;
-  LC_CUDA(c, cudaSetDevice(c->cfg.device));
+  LC_TRY(enter_host(c));
   timing_begin(c);
   if (S.synced != S.h_kf.size()) {  // the whole table again: views are appended rarely compared with rows
     LC_TRY(ensure(c, S.d_kf, S.h_kf.size() * sizeof(l2::L2Kf)));
@@ -1688,10 +1807,10 @@ LC_API int32_t lc_l2_loop_check(lc_ctx* c, const void* q, int32_t nq, size_t qs,
   LC_CUDA(c, cudaMemcpyAsync(c->d_l2frames.p, &fr, sizeof fr, cudaMemcpyHostToDevice, c->stream));
   LC_TRY(ensure(c, c->d_l2res, (size_t)n_kf * sizeof(l2::L2Result)));
   LC_TRY(ensure_pin_down(c, (size_t)n_kf * sizeof(l2::L2Result)));
-  LC_CUDA(c, cudaEventRecord(c->ev[1], c->stream));
+  if (c->timing_on) LC_CUDA(c, cudaEventRecord(c->ev[1], c->stream));
   LC_TRY(l2_run(c, (const l2::L2Kf*)S.d_kf.p, (int)n_kf, (const l2::L2Frame*)c->d_l2frames.p, &fr, 1, (l2::L2Result*)c->d_l2res.p,
                 l2::L2Knobs{loop_gap, min_rows, ratio}));
-  LC_CUDA(c, cudaEventRecord(c->ev[2], c->stream));
+  if (c->timing_on) LC_CUDA(c, cudaEventRecord(c->ev[2], c->stream));
   LC_CUDA(c, cudaMemcpyAsync(c->pin_down, c->d_l2res.p, (size_t)n_kf * sizeof(l2::L2Result), cudaMemcpyDeviceToHost, c->stream));
   LC_TRY(timing_end(c));
   static_assert(sizeof(lc_l2_result) == sizeof(l2::L2Result), "record layouts differ");
@@ -1709,7 +1828,7 @@ LC_API int32_t lc_get_last_timing(const lc_ctx* c, lc_timing* out) {
 LC_API int64_t lc_launch_count(const lc_ctx* c) { return c ? c->launches : 0; }
 LC_API int32_t lc_synchronize(lc_ctx* c) {
   if (!c) return LC_ERR_INVALID;
-  LC_CUDA(c, cudaSetDevice(c->cfg.device));
+  LC_TRY(enter_host(c));
   LC_CUDA(c, cudaStreamSynchronize(c->stream));
   return LC_OK;
 }

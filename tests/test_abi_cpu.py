@@ -69,7 +69,7 @@ def test_plain_c_client_compiles_links_and_runs(tmp_path):
                            os.path.join(ROOT, "examples", "abi_client.c"), lib, "-Wl,-rpath," + os.path.dirname(lib), "-o", exe])
     r = subprocess.run([exe], capture_output=True, text=True, timeout=120)
     assert r.returncode == 0, r.stdout + r.stderr
-    assert "liblc_b200 ABI 1" in r.stdout
+    assert "liblc_b200 ABI 2" in r.stdout
     assert ("no CPU fallback" in r.stdout) or ("keyframe 7 recognised with all matches" in r.stdout), r.stdout
 
 

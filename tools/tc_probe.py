@@ -10,7 +10,7 @@ c = lc.Context(kernel=kernel, loop_threshold=0.15)
 g = torch.Generator(device="cuda")
 g.manual_seed(1)
 rows = torch.randint(0, 256, (K * 2000, 32), dtype=torch.uint8, device="cuda", generator=g)
-c.db_append_many_device(np.arange(K, dtype=np.int32), np.full(K, 2000, np.int32), rows.data_ptr())
+c.db_append_many_device(np.arange(K, dtype=np.int32), np.full(K, 2000, np.int32), rows.data_ptr(), torch.cuda.current_stream().cuda_stream or 1)
 c.synchronize()
 q = np.random.default_rng(0).integers(0, 256, (2000, 32), np.uint8)
 for _ in range(3):
