@@ -226,6 +226,33 @@ int32_t lc_select_candidates(const lc_ctx* ctx, const lc_kf_result* results, int
 int32_t lc_detect_loops(lc_ctx* ctx, const uint8_t* q, int32_t nq, size_t q_stride, int32_t current_frame_id,
                         lc_loop_candidate* out, int64_t out_cap, int64_t* n_out);
 
+/* ---- processFrame's matcher side in ONE call (include/loop_closing.hpp:34, workflow README.md:94-102): for the frame
+ *      that ORB has just described,
+ *        matchFeatures(previous frame, this frame)   (query = the frame appended last, train = this one),
+ *        frames_.push_back(this frame)               (= lc_db_append), and
+ *        detectLoops(frame_id)                       (= lc_loop_check + lc_select_candidates)
+ *      behind ONE upload of the frame's rows - they land in the store, and both matches read them there - with the
+ *      table entries sent as kernel arguments, every launch queued back to back and one wait at the end.  Same results
+ *      as the three separate calls.  Unsharded contexts only.  train_idx / dist / good have `cap` entries, at least the
+ *      row count of the PREVIOUS frame (the query side); *n_matches = that count, or 0 for the first frame or an empty
+ *      side (then *min_dist = -1, *n_good = 0).  out[] receives the loop candidates in ascending keyframe order.
+ *      If the call fails after the append, *kf_index >= 0 says the frame is in the store. ---- */
+int32_t lc_process_frame(lc_ctx* ctx, int32_t frame_id, const uint8_t* desc, int32_t n, size_t row_stride,
+                         int32_t* train_idx, int32_t* dist, uint8_t* good, int32_t cap, int32_t* n_matches,
+                         int32_t* min_dist, int32_t* n_good, lc_loop_candidate* out, int64_t out_cap, int64_t* n_out,
+                         int64_t* kf_index);
+/* The same in three steps, so that the host's estimatePose / triangulatePoints (include/loop_closing.hpp:43-53) run on
+ * the pair matches WHILE the GPU is still scanning the store: _begin queues everything and returns; _matches (optional)
+ * waits for the pair match alone; _end waits for the loop check, hands out the candidates and - if results != NULL -
+ * the per-keyframe records (*n_results of them, one per stored keyframe including this frame).  Between _begin and
+ * _end the rules of lc_loop_check_begin apply. */
+int32_t lc_process_frame_begin(lc_ctx* ctx, int32_t frame_id, const uint8_t* desc, int32_t n, size_t row_stride,
+                               int64_t* kf_index);
+int32_t lc_process_frame_matches(lc_ctx* ctx, int32_t* train_idx, int32_t* dist, uint8_t* good, int32_t cap,
+                                 int32_t* n_matches, int32_t* min_dist, int32_t* n_good);
+int32_t lc_process_frame_end(lc_ctx* ctx, lc_loop_candidate* out, int64_t out_cap, int64_t* n_out,
+                             lc_kf_result* results, int64_t results_cap, int64_t* n_results);
+
 /* Merge step of a keyframe-sharded check (one process per GPU, store created with shard_rank / shard_world): every rank
  * lets lc_loop_check_batch_device write its records [n_frames][slots] and bests [rows] into ONE contribution buffer
  * [records | bests] of contrib_bytes (a multiple of 16), all-gathers the contributions (ncclAllGather) and calls this:

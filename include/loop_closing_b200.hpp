@@ -68,6 +68,7 @@ class HammingMatcher {
   void addFrame(int frame_id, const cv::Mat& descriptors) {
     check(descriptors);
     ok(lc_db_append(ctx_, frame_id, descriptors.data, descriptors.rows, descriptors.rows ? descriptors.step[0] : 32, nullptr));
+    last_rows_ = descriptors.rows;
   }
 
   // body of LoopClosingSystem::detectLoops(current_frame_id)
@@ -104,6 +105,39 @@ class HammingMatcher {
     return out;
   }
 
+  // The matcher side of a whole processFrame (include/loop_closing.hpp:34) in one GPU submission: matchFeatures(previous
+  // frame, this frame) + frames_.push_back + detectLoops(frame_id) behind a single upload of the descriptors.
+  //   beginFrame(id, desc);                                   // everything queued, returns at once
+  //   auto matches = frameMatches();                          // waits for the pair match only
+  //   estimatePose(prev, cur, matches, R, t); triangulatePoints(...);   // host, while the GPU scans the store
+  //   auto loops = finishFrame();                             // waits for the loop check
+  void beginFrame(int frame_id, const cv::Mat& descriptors) {
+    check(descriptors);
+    frame_prev_rows_ = last_rows_;
+    ok(lc_process_frame_begin(ctx_, frame_id, descriptors.data, descriptors.rows, descriptors.rows ? descriptors.step[0] : 32, nullptr));
+    last_rows_ = descriptors.rows;
+  }
+  std::vector<cv::DMatch> frameMatches() {
+    const int nq = frame_prev_rows_;
+    std::vector<int32_t> idx(nq), dist(nq);
+    std::vector<uint8_t> good(nq);
+    int32_t n = 0, min_dist = 0, n_good = 0;
+    ok(lc_process_frame_matches(ctx_, idx.data(), dist.data(), good.data(), nq, &n, &min_dist, &n_good));
+    std::vector<cv::DMatch> out;
+    out.reserve(n_good);
+    for (int i = 0; i < n; ++i)
+      if (good[i]) out.emplace_back(i, idx[i], 0, static_cast<float>(dist[i]));
+    return out;
+  }
+  std::vector<LoopCandidate> finishFrame() {
+    int64_t n_kf = 0, n = 0;
+    ok(lc_db_size(ctx_, &n_kf, nullptr, nullptr, nullptr));
+    std::vector<LoopCandidate> out(static_cast<size_t>(n_kf));
+    ok(lc_process_frame_end(ctx_, reinterpret_cast<lc_loop_candidate*>(out.data()), n_kf, &n, nullptr, 0, nullptr));
+    out.resize(static_cast<size_t>(n));
+    return out;
+  }
+
   // matchFeatures(current, frames_[k]) for the loop candidates in ONE call: the DMatch lists estimatePose /
   // triangulatePoints (include/loop_closing.hpp:43-53) verify a loop with.  kf_index[i] = position of the matched frame
   // in frames_ (the store shares its insertion order).
@@ -132,6 +166,7 @@ class HammingMatcher {
   }
   lc_ctx* ctx_ = nullptr;
   int pending_nq_ = 0, pending_id_ = 0;
+  int last_rows_ = 0, frame_prev_rows_ = 0;  // rows of the frame appended last / of the previous frame of the frame in flight
 };
 
 // The SHIPPED pipeline (src/main.cpp): matchFeatures (:509-534) and the matching step of its loop search (:1378-1392)

@@ -77,6 +77,10 @@ SYMBOLS = {
     "lc_loop_check_batch": (_i32, [_vp, _i32, _vp, _vp, _vp, _vp, _i64, _vp]),
     "lc_select_candidates": (_i32, [_vp, _vp, _i64, _i32, _i32, _vp, _i64, _pi64]),
     "lc_detect_loops": (_i32, [_vp, _vp, _i32, _sz, _i32, _vp, _i64, _pi64]),
+    "lc_process_frame": (_i32, [_vp, _i32, _vp, _i32, _sz, _vp, _vp, _vp, _i32, _pi32, _pi32, _pi32, _vp, _i64, _pi64, _pi64]),
+    "lc_process_frame_begin": (_i32, [_vp, _i32, _vp, _i32, _sz, _pi64]),
+    "lc_process_frame_matches": (_i32, [_vp, _vp, _vp, _vp, _i32, _pi32, _pi32, _pi32]),
+    "lc_process_frame_end": (_i32, [_vp, _vp, _i64, _pi64, _vp, _i64, _pi64]),
     "lc_loop_check_device": (_i32, [_vp, _vp, _i32, _i32, _vp, _vp, _vp]),
     "lc_loop_check_batch_device": (_i32, [_vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp]),
     "lc_merge_shards_device": (_i32, [_vp, _vp, _i64, _i32, _i32, _i64, _i64, _vp, _vp, _vp]),
@@ -398,6 +402,52 @@ class Context:
         n = C.c_int64()
         self._ck(self._lib.lc_detect_loops(self._h, _ptr(qa), len(qa), qs, int(current_frame_id), _ptr(out), cap, C.byref(n)))
         return out[:n.value]
+
+    # ---- processFrame: pair match vs the previous frame + append + loop check in one call
+    def _rows_of_last_keyframe(self):
+        k = self.db_size()["keyframes"]
+        if k == 0:
+            return 0
+        n, fid = C.c_int32(), C.c_int32()
+        self._ck(self._lib.lc_db_read(self._h, k - 1, None, 0, C.byref(n), C.byref(fid)))
+        return n.value
+
+    def process_frame(self, frame_id, desc):
+        """lc_process_frame.  Returns (pair, candidates, kf_index): pair as match_pair returns it (query = the previous
+        frame, train = this one; empty for the first frame), candidates a LOOP_CANDIDATE array."""
+        a, stride = _rows(desc)
+        n_prev = self._rows_of_last_keyframe()
+        idx, dist, good, nm, mn, ng = self._pair_out(n_prev)
+        cap = self.db_size()["local_keyframes"] + 1
+        out = np.zeros(cap, LOOP_CANDIDATE)
+        n_out, k = C.c_int64(), C.c_int64(-1)
+        self._ck(self._lib.lc_process_frame(self._h, int(frame_id), _ptr(a), len(a), stride, _ptr(idx), _ptr(dist), _ptr(good),
+                                            n_prev, C.byref(nm), C.byref(mn), C.byref(ng), _ptr(out), cap, C.byref(n_out), C.byref(k)))
+        return self._pair_ret(idx, dist, good, nm, mn, ng), out[:n_out.value], k.value
+
+    def process_frame_begin(self, frame_id, desc):
+        """Queue pair match + append + loop check of this frame and return at once; collect with process_frame_matches()
+        (optional, waits for the pair match only) and process_frame_end()."""
+        a, stride = _rows(desc)
+        self._frame_n_prev = self._rows_of_last_keyframe()
+        k = C.c_int64(-1)
+        self._ck(self._lib.lc_process_frame_begin(self._h, int(frame_id), _ptr(a), len(a), stride, C.byref(k)))
+        return k.value
+
+    def process_frame_matches(self):
+        idx, dist, good, nm, mn, ng = self._pair_out(self._frame_n_prev)
+        self._ck(self._lib.lc_process_frame_matches(self._h, _ptr(idx), _ptr(dist), _ptr(good), self._frame_n_prev, C.byref(nm), C.byref(mn),
+                                                    C.byref(ng)))
+        return self._pair_ret(idx, dist, good, nm, mn, ng)
+
+    def process_frame_end(self, want_records=False):
+        nloc = self.db_size()["local_keyframes"]
+        out = np.zeros(max(1, nloc), LOOP_CANDIDATE)
+        res = np.zeros(nloc, KF_RESULT) if want_records else None
+        n_out, n_res = C.c_int64(), C.c_int64()
+        self._ck(self._lib.lc_process_frame_end(self._h, _ptr(out), len(out), C.byref(n_out), _ptr(res) if want_records else None,
+                                                nloc, C.byref(n_res)))
+        return (out[:n_out.value], res[:n_res.value]) if want_records else out[:n_out.value]
 
     # ---- device-pointer variants (raw addresses; see sharded.py for the torch plumbing)
     def loop_check_device(self, d_q, nq, current_frame_id, d_results, d_best=None, stream=None):

@@ -96,6 +96,17 @@ struct lc_ctx {
     bool stashed = false, stashed_on = false;
     lc_timing stashed_timing{};
   } pending;
+  // lc_process_frame_begin / _matches / _end: the frame being processed (its loop check is `pending`)
+  struct FramePending {
+    bool active = false, pair_done = false, pair_direct = true;
+    int64_t kf_index = -1;
+    int32_t frame_id = 0, nq = 0, n_prev = 0;
+    bool matched = false;  // a pair kernel ran (both frames non-empty)
+  } frame;
+  uint8_t* pin_frame = nullptr;      // matchFeatures(prev, cur) results of the frame in flight
+  uint8_t* pin_frame_dev = nullptr;
+  size_t pin_frame_cap = 0;
+  cudaEvent_t pair_ev = nullptr;     // after the pair kernel of lc_process_frame_begin
   bool smem_attr_set = false;  // the tensor kernels' dynamic shared-memory limit has been raised on this device
   // ---- the SIFT / L2 store of the shipped pipeline's matcher (lc_l2.cuh): 128-byte rows + their squared norms
   struct L2Store {
@@ -932,6 +943,8 @@ LC_API void lc_destroy(lc_ctx* c) {
   if (c->pin_up) cudaFreeHost(c->pin_up);
   if (c->pin_down) cudaFreeHost(c->pin_down);
   if (c->pin_loop) cudaFreeHost(c->pin_loop);
+  if (c->pin_frame) cudaFreeHost(c->pin_frame);
+  if (c->pair_ev) cudaEventDestroy(c->pair_ev);
   for (auto& e : c->ev) if (e) cudaEventDestroy(e);
   for (auto& e : c->pin_ev) if (e) cudaEventDestroy(e);
   if (c->own_ev) cudaEventDestroy(c->own_ev);
@@ -982,6 +995,7 @@ LC_API int32_t lc_create(const lc_config* cfg, lc_ctx** out) {
     cudaEventRecord(ev, c->stream);
   }
   if ((e = cudaEventCreateWithFlags(&c->own_ev, cudaEventDisableTiming)) != cudaSuccess) return bail("cudaEventCreate", e);
+  if ((e = cudaEventCreateWithFlags(&c->pair_ev, cudaEventDisableTiming)) != cudaSuccess) return bail("cudaEventCreate", e);
   if ((e = cudaEventCreateWithFlags(&c->foreign_ev, cudaEventDisableTiming)) != cudaSuccess) return bail("cudaEventCreate", e);
   if ((e = cudaMallocHost((void**)&c->pin_up, 2 * kPinHalfBytes)) != cudaSuccess) return bail("cudaMallocHost", e);
   *out = c;
@@ -1521,6 +1535,7 @@ LC_API int32_t lc_loop_check_begin(lc_ctx* c, const uint8_t* q, int32_t nq, size
 LC_API int32_t lc_loop_check_end(lc_ctx* c, lc_kf_result* results, int64_t results_cap, int64_t* n_results, uint64_t* best_packed) {
   if (!c) return LC_ERR_INVALID;
   LC_GUARD_BEGIN
+  if (c->frame.active) return fail(c, LC_ERR_INVALID, "a frame is pending: call lc_process_frame_end");
   if (n_results) *n_results = c->pending.active ? c->pending.n_res : 0;
   return loop_check_collect(c, results, results_cap, best_packed);
   LC_GUARD_END(c)
@@ -1571,6 +1586,194 @@ LC_API int32_t lc_detect_loops(lc_ctx* c, const uint8_t* q, int32_t nq, size_t q
   const int rc = lc_select_candidates(c, res.data(), n, nq, cur_id, out, out_cap, n_out);
   if (rc == LC_ERR_CAPACITY) return fail(c, rc, "out_cap %lld too small", (long long)out_cap);
   return rc;
+  LC_GUARD_END(c)
+}
+
+// ------------------------------------------------------------------- processFrame (include/loop_closing.hpp:34)
+namespace {
+
+// first half of lc_process_frame: append + matchFeatures(previous frame, this frame) + loop check, all queued on the
+// context's stream behind ONE upload of the frame's rows (they land in the store; the pair match and the loop check read
+// them there), nothing waited for
+int process_frame_enqueue(lc_ctx* c, int32_t frame_id, const uint8_t* desc, int32_t n, size_t stride, bool pair_event, int64_t* kf_index) {
+  if (c->cfg.shard_world != 1) return fail(c, LC_ERR_INVALID, "lc_process_frame needs an unsharded context (the previous frame must be resident here)");
+  if (c->pending.active || c->frame.active) return fail(c, LC_ERR_INVALID, "a loop check or a frame is pending: call lc_loop_check_end / lc_process_frame_end first");
+  LC_TRY(check_rows(c, "frame", desc, n, stride));
+  LC_TRY(enter_host(c));
+  const bool had_prev = !c->h_kf.empty();
+  const KfEntry prev = had_prev ? c->h_kf.back() : KfEntry{nullptr, 0, 0, 0};
+  const int64_t n_kf_before = (int64_t)c->h_kf.size();
+  const int64_t rows_total = (int64_t)n;
+  timing_begin(c, loop_events(c, rows_total));
+  // ---- frames_.push_back: the rows go to their place in the store (the call's only bulk upload)
+  int64_t k = -1;
+  LC_TRY(store_append(c, frame_id, desc, n, stride, false, &k));
+  if (kf_index) *kf_index = k;
+  const KfEntry cur = c->h_kf.back();
+  const int64_t n_kf = n_kf_before + 1;
+  c->frame = lc_ctx::FramePending{};
+  c->frame.kf_index = k;
+  c->frame.frame_id = frame_id;
+  c->frame.nq = n;
+  c->frame.n_prev = prev.n;
+  // ---- the two table entries of this frame: the keyframe table's new slot and the query-frame record, by kernel argument
+  LC_TRY(ensure(c, c->d_frames, sizeof(QFrame)));
+  const QFrame qf{cur.rows, n, frame_id, nullptr};
+  if ((size_t)n_kf * sizeof(KfEntry) <= c->d_kf.cap && c->d_kf_synced == (size_t)n_kf_before) {
+    poke_tables_kernel<<<1, 32, 0, c->stream>>>((KfEntry*)c->d_kf.p + n_kf_before, cur, (QFrame*)c->d_frames.p, qf);
+    c->d_kf_synced = (size_t)n_kf;
+  } else {  // the table has to grow (or was never uploaded): the ordinary road, then the frame record alone
+    LC_TRY(sync_kf_table(c));
+    poke_tables_kernel<<<1, 32, 0, c->stream>>>(nullptr, cur, (QFrame*)c->d_frames.p, qf);
+  }
+  LC_CUDA(c, cudaGetLastError());
+  c->launches += 1;
+  c->timing.kernel_launches += 1;
+  if (c->timing_on) LC_CUDA(c, cudaEventRecord(c->ev[1], c->stream));
+  // ---- matchFeatures(prev, cur): query = the previous frame (resident), train = this frame (include/loop_closing.hpp:40,
+  //      direction as src/main.cpp:1154)
+  if (had_prev && prev.n > 0 && n > 0) {
+    const int32_t nq = prev.n;
+    const size_t off_dist = (size_t)nq * 4, off_sum = off_dist + (size_t)nq * 4, off_good = off_sum + 8, out_bytes = off_good + (size_t)nq;
+    c->frame.pair_direct = out_bytes <= kPairDirectOutBytes;
+    LC_TRY(ensure_pinned(c, c->pin_frame, c->pin_frame_dev, c->pin_frame_cap, out_bytes));
+    if (!c->frame.pair_direct) LC_TRY(ensure(c, c->d_out, out_bytes));
+    uint8_t* d = c->frame.pair_direct ? c->pin_frame_dev : (uint8_t*)c->d_out.p;
+    const int path_before = c->timing.path;
+    LC_TRY(pair_device_impl(c, c->stream, prev.rows, nq, cur, PairOut{(int32_t*)d, (int32_t*)(d + off_dist), d + off_good, (int32_t*)(d + off_sum)}));
+    c->timing.path = path_before;  // the call reports the loop check's path
+    if (!c->frame.pair_direct) LC_CUDA(c, cudaMemcpyAsync(c->pin_frame, d, out_bytes, cudaMemcpyDeviceToHost, c->stream));
+    if (pair_event) LC_CUDA(c, cudaEventRecord(c->pair_ev, c->stream));
+    c->frame.matched = true;
+  }
+  // ---- detectLoops(frame_id): this frame, read where it now lives in the store, against every stored keyframe (itself
+  //      included when min_loop_gap <= 0, as frames_ holds it by then: include/loop_closing.hpp:69, README.md:94-102)
+  c->pending = lc_ctx::Pending{};
+  c->pending.active = true;
+  c->pending.n_res = n_kf;
+  c->pending.rows = n;
+  const size_t res_bytes = (size_t)n_kf * sizeof(lc_kf_result);
+  LC_TRY(ensure(c, c->d_results, std::max<size_t>(res_bytes, 16)));
+  LC_TRY(ensure_pin_loop(c, res_bytes + 16));
+  std::vector<QFrame> hf(1, qf);
+  LC_TRY(run_match(c, c->stream, (const KfEntry*)c->d_kf.p, (int)n_kf, c->max_n_local, (const QFrame*)c->d_frames.p, hf.data(), 1,
+                   (lc_kf_result*)c->d_results.p, knobs_of(c->cfg), c->n_partial_kf == 0, nullptr, 0));
+  if (c->timing_on) LC_CUDA(c, cudaEventRecord(c->ev[2], c->stream));
+  LC_CUDA(c, cudaMemcpyAsync(c->pin_loop, c->d_results.p, res_bytes, cudaMemcpyDeviceToHost, c->stream));
+  if (c->timing_on) LC_CUDA(c, cudaEventRecord(c->ev[3], c->stream));
+  c->pending.res_bytes = res_bytes;
+  c->pending.queued = true;
+  c->frame.active = true;
+  return LC_OK;
+}
+
+// matchFeatures(prev, cur) of the frame in flight; wait_all: the whole stream has been waited for already
+int process_frame_matches(lc_ctx* c, bool wait_all, int32_t* train_idx, int32_t* dist, uint8_t* good, int32_t cap, int32_t* n_matches,
+                          int32_t* min_dist, int32_t* n_good) {
+  if (!c->frame.matched) {  // first frame, or an empty side: cv::BFMatcher returns no matches
+    empty_pair(n_matches, min_dist, n_good);
+    return LC_OK;
+  }
+  const int32_t nq = c->frame.n_prev;
+  if ((train_idx || dist || good) && cap < nq) return fail(c, LC_ERR_CAPACITY, "cap %d < %d rows of the previous frame", cap, nq);
+  if (!wait_all && !c->frame.pair_done) LC_CUDA(c, cudaEventSynchronize(c->pair_ev));
+  c->frame.pair_done = true;
+  const size_t off_dist = (size_t)nq * 4, off_sum = off_dist + (size_t)nq * 4, off_good = off_sum + 8;
+  const uint8_t* h = c->pin_frame;
+  if (train_idx) memcpy(train_idx, h, (size_t)nq * 4);
+  if (dist) memcpy(dist, h + off_dist, (size_t)nq * 4);
+  if (good) memcpy(good, h + off_good, (size_t)nq);
+  int32_t sum[2];
+  memcpy(sum, h + off_sum, 8);
+  if (n_matches) *n_matches = nq;
+  if (min_dist) *min_dist = sum[0];
+  if (n_good) *n_good = sum[1];
+  return LC_OK;
+}
+
+int process_frame_collect(lc_ctx* c, lc_loop_candidate* out, int64_t out_cap, int64_t* n_out, lc_kf_result* results, int64_t results_cap,
+                          int64_t* n_results) {
+  if (!c->frame.active) return fail(c, LC_ERR_INVALID, "no frame is pending");
+  const lc_ctx::FramePending fr = c->frame;
+  const int64_t n_res = c->pending.n_res;
+  if (n_results) *n_results = n_res;
+  c->frame.active = false;
+  // the records stay in the pinned buffer: select from there, copy out only when asked to
+  const bool want_records = results != nullptr;
+  if (want_records && results_cap < n_res) {
+    c->frame.active = true;  // nothing consumed: the caller may come back with room
+    return fail(c, LC_ERR_CAPACITY, "results_cap %lld < %lld", (long long)results_cap, (long long)n_res);
+  }
+  {  // wait; with results == NULL the collect step must not insist on a destination
+    const lc_ctx::Pending p = c->pending;
+    c->pending.active = false;
+    if (p.stashed) {
+      c->timing = p.stashed_timing;
+      c->timing_on = p.stashed_on;
+    }
+    if (p.queued) LC_TRY(timing_end(c, true, false));
+    if (want_records && p.res_bytes) memcpy(results, c->pin_loop, p.res_bytes);
+  }
+  c->frame.pair_done = true;  // the stream has drained
+  int64_t n = 0;
+  const int rc = lc_select_candidates(c, (const lc_kf_result*)c->pin_loop, n_res, fr.nq, fr.frame_id, out, out_cap, &n);
+  if (n_out) *n_out = n;
+  if (rc == LC_ERR_CAPACITY) return fail(c, rc, "out_cap %lld < %lld loop candidates", (long long)out_cap, (long long)n);
+  return rc;
+}
+
+}  // namespace
+
+LC_API int32_t lc_process_frame_begin(lc_ctx* c, int32_t frame_id, const uint8_t* desc, int32_t n, size_t stride, int64_t* kf_index) {
+  if (!c) return LC_ERR_INVALID;
+  LC_GUARD_BEGIN
+  if (kf_index) *kf_index = -1;
+  const int rc = process_frame_enqueue(c, frame_id, desc, n, stride, true, kf_index);
+  if (rc != LC_OK && !c->frame.active) {  // nothing of a failed frame stays pending (an appended keyframe stays appended)
+    if (c->pending.active && !c->pending.queued) c->pending.active = false;
+    c->frame = lc_ctx::FramePending{};
+  }
+  return rc;
+  LC_GUARD_END(c)
+}
+
+LC_API int32_t lc_process_frame_matches(lc_ctx* c, int32_t* train_idx, int32_t* dist, uint8_t* good, int32_t cap, int32_t* n_matches,
+                                        int32_t* min_dist, int32_t* n_good) {
+  if (!c) return LC_ERR_INVALID;
+  LC_GUARD_BEGIN
+  if (!c->frame.active) return fail(c, LC_ERR_INVALID, "no frame is pending");
+  LC_CUDA(c, cudaSetDevice(c->cfg.device));
+  return process_frame_matches(c, false, train_idx, dist, good, cap, n_matches, min_dist, n_good);
+  LC_GUARD_END(c)
+}
+
+LC_API int32_t lc_process_frame_end(lc_ctx* c, lc_loop_candidate* out, int64_t out_cap, int64_t* n_out, lc_kf_result* results,
+                                    int64_t results_cap, int64_t* n_results) {
+  if (!c) return LC_ERR_INVALID;
+  LC_GUARD_BEGIN
+  LC_CUDA(c, cudaSetDevice(c->cfg.device));
+  return process_frame_collect(c, out, out_cap, n_out, results, results_cap, n_results);
+  LC_GUARD_END(c)
+}
+
+LC_API int32_t lc_process_frame(lc_ctx* c, int32_t frame_id, const uint8_t* desc, int32_t n, size_t stride, int32_t* train_idx, int32_t* dist,
+                                uint8_t* good, int32_t cap, int32_t* n_matches, int32_t* min_dist, int32_t* n_good, lc_loop_candidate* out,
+                                int64_t out_cap, int64_t* n_out, int64_t* kf_index) {
+  if (!c) return LC_ERR_INVALID;
+  LC_GUARD_BEGIN
+  if (kf_index) *kf_index = -1;
+  if (!c->h_kf.empty() && (train_idx || dist || good) && cap < c->h_kf.back().n)  // before anything is appended
+    return fail(c, LC_ERR_CAPACITY, "cap %d < %d rows of the previous frame", cap, c->h_kf.back().n);
+  int rc = process_frame_enqueue(c, frame_id, desc, n, stride, false, kf_index);
+  if (rc != LC_OK) {
+    if (c->pending.active && !c->pending.queued) c->pending.active = false;
+    if (!c->frame.active) c->frame = lc_ctx::FramePending{};
+    return rc;
+  }
+  // one wait for everything; the candidates first (that drains the stream), then the matches from their pinned buffer
+  rc = process_frame_collect(c, out, out_cap, n_out, nullptr, 0, nullptr);
+  const int rc2 = process_frame_matches(c, true, train_idx, dist, good, cap, n_matches, min_dist, n_good);
+  return rc != LC_OK ? rc : rc2;
   LC_GUARD_END(c)
 }
 

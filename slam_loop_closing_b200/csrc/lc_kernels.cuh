@@ -468,4 +468,14 @@ __global__ void fill_u64_kernel(uint64_t* p, size_t n, uint64_t v) {
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) p[i] = v;
 }
 
+// Table entries that change with every frame travel as kernel ARGUMENTS: a launch carries them to the device for a few
+// microseconds, where a host-to-device copy of 24 bytes costs a copy-engine start-up and (from pageable memory) a
+// staging step.  lc_process_frame puts the new keyframe's table entry and the query-frame record in place with it.
+__global__ void poke_tables_kernel(KfEntry* kf_slot, KfEntry kf, QFrame* frame_slot, QFrame frame) {
+  if (threadIdx.x == 0) {
+    if (kf_slot) *kf_slot = kf;
+    if (frame_slot) *frame_slot = frame;
+  }
+}
+
 }  // namespace lc

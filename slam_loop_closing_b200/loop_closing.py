@@ -73,6 +73,16 @@ class B200Matcher:
     def match_keyframes(self, q, kf_indices):
         return self.ctx.match_keyframes(q, kf_indices)
 
+    # the matcher side of a whole processFrame in one GPU submission (lc_process_frame_begin / _matches / _end)
+    def frame_begin(self, frame_id, descriptors):
+        return self.ctx.process_frame_begin(frame_id, descriptors)
+
+    def frame_matches(self):
+        return self.ctx.process_frame_matches()
+
+    def frame_end(self):
+        return self.ctx.process_frame_end()
+
     def close(self):
         self.ctx.close()
 
@@ -82,7 +92,7 @@ class LoopClosingSystem:
 
     def __init__(self, loop_threshold: float = 0.7, min_loop_gap: int = 30, *, matcher=None, nfeatures: int = 2000,
                  min_good: int = 50, filter_floor: int = 0, filter_strict: bool = False, min_init: int = -1,
-                 gap_strict: bool = False, thr_inclusive: bool = False, device: int = 0):
+                 gap_strict: bool = False, thr_inclusive: bool = False, device: int = 0, fused: bool = True):
         self.loop_threshold_ = float(loop_threshold)
         self.min_loop_gap_ = int(min_loop_gap)
         self.min_good_ = int(min_good)
@@ -91,6 +101,7 @@ class LoopClosingSystem:
         self.loop_closures_: List[LoopCandidate] = []
         self.consecutive_matches_: List[int] = []  # good-match count of every (prev, cur) pair, for tests
         self.nfeatures_ = nfeatures
+        self.fused_ = bool(fused)  # one GPU submission per frame (lc_process_frame_*) when the matcher offers it
         self.feature_detector_ = None  # cv::ORB, created on first use (include/loop_closing.hpp:72)
         # the matcher_ of include/loop_closing.hpp:73; anything with match_pair/append/loop_check fits
         self.matcher_ = matcher if matcher is not None else B200Matcher(
@@ -112,9 +123,14 @@ class LoopClosingSystem:
         return self._process(frame, geometry=False)
 
     def _process(self, frame: Frame, geometry: bool) -> List[LoopCandidate]:
+        fused = self.fused_ and hasattr(self.matcher_, "frame_begin")
+        if fused:
+            # one GPU submission for the frame: pair match vs the previous frame, append, loop check.  The pose stages
+            # below run on the host while the GPU is still scanning the store.
+            self.matcher_.frame_begin(frame.id, frame.descriptors)
         if self.frames_:  # README.md:96-100
             prev = self.frames_[-1]
-            matches = self.matchFeatures(prev, frame)
+            matches = self._dmatches(self.matcher_.frame_matches()) if fused else self.matchFeatures(prev, frame)
             self.consecutive_matches_.append(len(matches))
             if geometry and len(matches) >= 8:  # README.md:132
                 ok, R, t = self.estimatePose(prev, frame, matches)
@@ -124,8 +140,12 @@ class LoopClosingSystem:
                     frame.pose = prev.pose @ np.linalg.inv(T)
                     frame.points3D = self.triangulatePoints(prev, frame, matches)
         self.frames_.append(frame)  # hpp:69 - and the device store gets the descriptors
-        self.matcher_.append(frame.id, frame.descriptors)
-        loops = self.detectLoops(frame.id)
+        if fused:
+            loops = [LoopCandidate(int(c["current_frame_id"]), int(c["matched_frame_id"]), int(c["num_matches"]),
+                                   float(c["similarity_score"])) for c in self.matcher_.frame_end()]
+        else:
+            self.matcher_.append(frame.id, frame.descriptors)
+            loops = self.detectLoops(frame.id)
         self.loop_closures_.extend(loops)
         return loops
 
@@ -169,9 +189,12 @@ class LoopClosingSystem:
         return cv2.drawMatches(frame1.image, frame1.keypoints, frame2.image, frame2.keypoints, cvm, None)
 
     # ------------------------------------------------------------------ the hot path (GPU)
-    def matchFeatures(self, frame1: Frame, frame2: Frame) -> List[DMatch]:  # hpp:40, README.md:116-117
-        r = self.matcher_.match_pair(frame1.descriptors, frame2.descriptors)
+    @staticmethod
+    def _dmatches(r) -> List[DMatch]:
         return [DMatch(int(i), int(r["train_idx"][i]), 0, float(r["dist"][i])) for i in np.flatnonzero(r["good"])]
+
+    def matchFeatures(self, frame1: Frame, frame2: Frame) -> List[DMatch]:  # hpp:40, README.md:116-117
+        return self._dmatches(self.matcher_.match_pair(frame1.descriptors, frame2.descriptors))
 
     def detectLoops(self, current_frame_id: int) -> List[LoopCandidate]:  # hpp:48, README.md:121-126
         cur = next((f for f in reversed(self.frames_) if f.id == current_frame_id), None)

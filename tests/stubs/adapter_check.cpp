@@ -10,12 +10,15 @@ int main() {
     m.beginDetectLoops(1, d);
     auto l2 = m.finishDetectLoops();
     auto c = m.matchCandidates(d, {0});
+    m.beginFrame(2, d);
+    auto fm = m.frameMatches();
+    auto fl = m.finishFrame();
     loop_closing::b200::SiftMatcher s;
     std::vector<cv::DMatch> good;
     s.matchFeatures(d, d, good, 0.75);
     s.addView(0, d);
     auto r = s.loopMatchCounts(d, 5, 3);
-    return static_cast<int>(g.size() + l.size() + l2.size() + c.size() + good.size() + r.size());
+    return static_cast<int>(fm.size() + fl.size() + g.size() + l.size() + l2.size() + c.size() + good.size() + r.size());
   } catch (const std::exception&) {
     return 0;  // no B200 here: lc_create throws, which is the point of "no CPU fallback"
   }

@@ -77,10 +77,12 @@ def test_orb_loop_sequence_equals_golden(lc, kernel):
     assert np.array_equal(np.array([tuple(float(v) for v in x) for x in cands], np.float64).reshape(-1, 4), want)
 
 
-def test_loop_closing_system_twin_equals_golden(lc):
-    """the same sequence through the LoopClosingSystem mirror (include/loop_closing.hpp:29-66)."""
+@pytest.mark.parametrize("fused", [True, False])
+def test_loop_closing_system_twin_equals_golden(lc, fused):
+    """the same sequence through the LoopClosingSystem mirror (include/loop_closing.hpp:29-66): one GPU submission per
+    frame (lc_process_frame_begin / _matches / _end) or the three separate calls."""
     descs, p = _orb_case()
-    s = lc.LoopClosingSystem(p.loop_threshold, p.min_loop_gap, min_good=p.min_good, filter_floor=p.filter_floor)
+    s = lc.LoopClosingSystem(p.loop_threshold, p.min_loop_gap, min_good=p.min_good, filter_floor=p.filter_floor, fused=fused)
     for i, d in enumerate(descs):
         loops = s.processDescriptors(d, i)
         if loops:  # the candidates' DMatch lists in one GPU call: sizes equal the candidates' match counts
