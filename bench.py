@@ -426,7 +426,7 @@ def main():
         if n_kf >= 1000:  # BASELINE config 5 in shape, on this GPU's resident DB: 64 query frames in one batched check
             import datagen
             frames = [q] + [datagen.uniform(NQ, 7000 + i) for i in range(63)]
-            ctx.loop_check_batch(frames[:4], [cur_id] * 4)
+            ctx.loop_check_batch(frames, [cur_id] * 64)  # first call of this shape: result buffers (102 MB pinned) grow
             t0 = time.perf_counter()
             res, _ = ctx.loop_check_batch(frames, [cur_id] * 64)
             dt = time.perf_counter() - t0

@@ -429,15 +429,16 @@ class Context:
         """Queue pair match + append + loop check of this frame and return at once; collect with process_frame_matches()
         (optional, waits for the pair match only) and process_frame_end()."""
         a, stride = _rows(desc)
-        self._frame_n_prev = self._rows_of_last_keyframe()
+        n_prev = self._rows_of_last_keyframe()
         k = C.c_int64(-1)
         self._ck(self._lib.lc_process_frame_begin(self._h, int(frame_id), _ptr(a), len(a), stride, C.byref(k)))
+        self._frame_n_prev = n_prev  # rows of the previous frame = entries of the pair-match outputs of the frame in flight
         return k.value
 
     def process_frame_matches(self):
-        idx, dist, good, nm, mn, ng = self._pair_out(self._frame_n_prev)
-        self._ck(self._lib.lc_process_frame_matches(self._h, _ptr(idx), _ptr(dist), _ptr(good), self._frame_n_prev, C.byref(nm), C.byref(mn),
-                                                    C.byref(ng)))
+        n_prev = getattr(self, "_frame_n_prev", 0)
+        idx, dist, good, nm, mn, ng = self._pair_out(n_prev)
+        self._ck(self._lib.lc_process_frame_matches(self._h, _ptr(idx), _ptr(dist), _ptr(good), n_prev, C.byref(nm), C.byref(mn), C.byref(ng)))
         return self._pair_ret(idx, dist, good, nm, mn, ng)
 
     def process_frame_end(self, want_records=False):

@@ -15,12 +15,21 @@ c.synchronize()
 rng = np.random.default_rng(0)
 qs = [rng.integers(0, 256, (2000, 32), np.uint8) for _ in range(F)]
 cur = [K + 100] * F
-for _ in range(2):
+import time
+for i in range(2):
+    t0 = time.perf_counter()
     res, best = c.loop_check_batch(qs, cur)
+    tm = c.last_timing()
+    print(f"warm-up call {i}: wall {(time.perf_counter() - t0) * 1e3:.1f} ms; h2d {tm.h2d_ms:.2f} kernels {tm.kernel_ms:.1f} (match {tm.match_ms:.1f} in "
+          f"{tm.match_launches}) d2h {tm.d2h_ms:.2f} total {tm.total_ms:.1f}", flush=True)
 ks = []
 for _ in range(3):
+    t0 = time.perf_counter()
     c.loop_check_batch(qs, cur)
-    ks.append(c.last_timing().kernel_ms)
+    tm = c.last_timing()
+    ks.append(tm.kernel_ms)
+    print(f"call: wall {(time.perf_counter() - t0) * 1e3:.1f} ms; h2d {tm.h2d_ms:.2f} kernels {tm.kernel_ms:.1f} (match {tm.match_ms:.1f} in "
+          f"{tm.match_launches}) d2h {tm.d2h_ms:.2f} total {tm.total_ms:.1f}", flush=True)
 r1, b1 = c.loop_check(qs[F // 2], K + 100)
 assert np.array_equal(res[F // 2], r1) and np.array_equal(best[F // 2], b1), "batch != single"
 print("kernel", kernel, "K", K, "F", F, "kernel_ms", float(np.median(ks)), "Gpairs/s", 2000 * 2000 * K * F / float(np.median(ks)) / 1e6,
