@@ -455,14 +455,17 @@ def c1_sequence(lc, kernel, n_frames=97, cpu_frames=8):
     frames = [datagen.uniform(2000, 900 + i) for i in range(n_frames)]
     p = Params(loop_threshold=0.15, min_loop_gap=30)
 
-    def run(c):
+    def run(c, fused=False):
         per = []
         for i, d in enumerate(frames):
             t0 = time.perf_counter()
-            if i:
-                c.match_pair(frames[i - 1], d)
-            c.db_append(i, d)
-            c.loop_check(d, i, want_best=False)
+            if fused:  # lc_process_frame: one upload, one GPU submission, one wait per frame
+                c.process_frame(i, d)
+            else:
+                if i:
+                    c.match_pair(frames[i - 1], d)
+                c.db_append(i, d)
+                c.loop_check(d, i, want_best=False)
             per.append(time.perf_counter() - t0)
         return per
 
@@ -470,11 +473,18 @@ def c1_sequence(lc, kernel, n_frames=97, cpu_frames=8):
         run(c)  # warm-up pass (buffer growth, first launches)
     with lc.Context(kernel=kernel, loop_threshold=p.loop_threshold, min_loop_gap=p.min_loop_gap) as c:
         per = run(c)
+    with lc.Context(kernel=kernel, loop_threshold=p.loop_threshold, min_loop_gap=p.min_loop_gap) as c:
+        run(c, True)
+    with lc.Context(kernel=kernel, loop_threshold=p.loop_threshold, min_loop_gap=p.min_loop_gap) as c:
+        per_fused = run(c, True)
     pair_matches = (n_frames - 1) + sum(max(0, i - 29) for i in range(n_frames))  # consecutive + eligible loop matches
     out = {"gpu_ms_total": float(np.sum(per) * 1e3), "gpu_us_per_frame_median": float(np.median(per) * 1e6),
            "gpu_us_last_frame": float(per[-1] * 1e6), "pair_matches": pair_matches,
            "gpu_gpairs_s": pair_matches * 4e6 / float(np.sum(per)) / 1e9,
-           "api": "lc_match_pair + lc_db_append + lc_loop_check per frame (ctypes, host buffers)"}
+           "api": "lc_match_pair + lc_db_append + lc_loop_check per frame (ctypes, host buffers)",
+           "fused": {"gpu_ms_total": float(np.sum(per_fused) * 1e3), "gpu_us_per_frame_median": float(np.median(per_fused) * 1e6),
+                     "gpu_us_last_frame": float(per_fused[-1] * 1e6), "gpu_gpairs_s": pair_matches * 4e6 / float(np.sum(per_fused)) / 1e9,
+                     "api": "lc_process_frame per frame: pair match vs the resident previous frame + append + loop check in one submission"}}
     if cv2_ref.available():
         import cv2
         cv2.setNumThreads(os.cpu_count() or 1)
