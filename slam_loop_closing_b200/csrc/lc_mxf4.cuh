@@ -1,8 +1,8 @@
 // lc_mxf4.cuh - Hamming matching on the FP4 tensor pipe (tcgen05.mma kind::mxf4.block_scale, TMEM).
 //
-// Identity: descriptor bits mapped to E2M1 +1.0 / -1.0 (all UE8M0 block scales = 1.0) give
-//     D[q][t] = 256 - 2 * hamming(q, t)          (f32 accumulation of <= 256 terms of +/-1: exact),
-// so min_t hamming = (256 - max_t D) / 2.  kind::mxf4 runs 16384 MAC/clk/SM = 64 descriptor pairs/clk/SM, twice
+// Identity: query bits mapped to E2M1 -1.0 / +1.0 and train bits to 0.0 / +1.0 (all UE8M0 block scales = 1.0) give
+//     D[q][t] = 2 popc(q & t) - popc(t) = popc(q) - hamming(q, t)     (f32 accumulation of <= 256 terms of 0, +/-1: exact),
+// so min_t hamming = popc(q) - max_t D  (the +1 / -1 form of both sides, D = 256 - 2 hamming, is kept behind a macro).  kind::mxf4 runs 16384 MAC/clk/SM = 64 descriptor pairs/clk/SM, twice
 // kind::i8 and 32x the POPC pipe (measured: tools/umma_fp4.cu, profiles/r01_umma_fp4_probe.txt).
 //
 // What this kernel produces is the per-(keyframe, query) MINIMUM DISTANCE only.  That is all the loop check needs per
@@ -79,12 +79,25 @@ struct ABlock {          // one resident query block: up to 1024 queries of one 
 using tc::CtaWork;
 
 // ---------------------------------------------------------------- bit -> E2M1 expansion
-// 32 descriptor bits -> 32 E2M1 nibbles (one 16-byte swizzle chunk): bit clear -> +1.0 (0x2), bit set -> -1.0 (0xA).
-// PRMT is the lookup: a selector nibble holding two descriptor bits picks the byte (two E2M1 values) from the pool
-// {0x22, 0x2A, 0xA2, 0xAA}.  The resulting order of the 256 values along K is a fixed permutation of the bit order -
-// irrelevant for a dot product as long as queries and train rows use the same one.
+// 32 descriptor bits -> 32 E2M1 nibbles (one 16-byte swizzle chunk).  PRMT is the lookup: a selector nibble holding two
+// descriptor bits picks the byte (two E2M1 values) from a four-byte pool.  The resulting order of the 256 values along K
+// is a fixed permutation of the bit order - irrelevant for a dot product as long as queries and train rows use the same
+// one.  Two encodings (LC_FX_ZERO_ONE_TRAIN):
+//   1 (default)  queries: bit clear -> -1.0 (0xA), set -> +1.0 (0x2);  train rows: clear -> 0.0 (0x0), set -> +1.0 (0x2):
+//                D = 2 popc(q & t) - popc(t) = popc(q) - hamming(q, t), so min_t hamming = popc(q) - max_t D.  popc(q) is a
+//                per-QUERY constant added once per (keyframe, query) result, and half of all products are exact zeros -
+//                the multipliers and adders they would toggle are what a power-capped B200 spends its clock on.
+//   0            both sides +1.0 / -1.0:  D = 256 - 2 hamming.
+#ifndef LC_FX_ZERO_ONE_TRAIN
+#define LC_FX_ZERO_ONE_TRAIN 1
+#endif
+template <bool QUERY>
 __device__ __forceinline__ uint4 expand_word_fp4(uint32_t x) {
+#if LC_FX_ZERO_ONE_TRAIN
+  constexpr uint32_t pool = QUERY ? 0x222AA2AAu : 0x22200200u;  // bytes for the bit pairs 00, 01, 10, 11 (low nibble = low bit)
+#else
   constexpr uint32_t pool = 0xAAA22A22u;
+#endif
   const uint32_t lo = x & 0x33333333u, hi = (x >> 2) & 0x33333333u;
   return make_uint4(__byte_perm(pool, 0u, lo & 0xffffu), __byte_perm(pool, 0u, lo >> 16), __byte_perm(pool, 0u, hi & 0xffffu),
                     __byte_perm(pool, 0u, hi >> 16));
@@ -116,8 +129,11 @@ __global__ void __launch_bounds__(kExpandThreads)
   uint8_t* img = img_base + (size_t)blockIdx.x * kABytes + (size_t)tile * kATileBytes;
   for (int idx = threadIdx.x; idx < kQTile * 8; idx += kExpandThreads) {
     const int r = idx >> 3, w = idx & 7, q = ab.q0 + tile * kQTile + r;
-    const uint32_t bits = tile * kQTile + r < ab.nq ? __ldg(reinterpret_cast<const uint32_t*>(fr.q) + (size_t)q * 8 + w) : 0u;
-    *reinterpret_cast<uint4*>(img + tile_offset(r, w)) = expand_word_fp4(bits);
+    // rows past the end of the block: E2M1 0.0 everywhere - their products are exact zeros that cost the tensor pipe no
+    // switching power (their accumulator rows are never read)
+    const bool valid = tile * kQTile + r < ab.nq;
+    const uint4 e = valid ? expand_word_fp4<true>(__ldg(reinterpret_cast<const uint32_t*>(fr.q) + (size_t)q * 8 + w)) : make_uint4(0u, 0u, 0u, 0u);
+    *reinterpret_cast<uint4*>(img + tile_offset(r, w)) = e;
   }
   if (fill_best && fr.best_packed && threadIdx.x < kQTile) {
     const int q = ab.q0 + tile * kQTile + threadIdx.x;
@@ -388,8 +404,8 @@ __global__ void __launch_bounds__(kThreads, 1)
 #pragma unroll
         for (int i = 0; i < kPairsPerExpThread; ++i) {
           if (r0 + 32 * i < rows_used) {
-            *reinterpret_cast<uint4*>(tile + off_lo + i * 4096) = expand_word_fp4(bits[i].x);
-            *reinterpret_cast<uint4*>(tile + off_hi + i * 4096) = expand_word_fp4(bits[i].y);
+            *reinterpret_cast<uint4*>(tile + off_lo + i * 4096) = expand_word_fp4<false>(bits[i].x);
+            *reinterpret_cast<uint4*>(tile + off_hi + i * 4096) = expand_word_fp4<false>(bits[i].y);
           }
         }
         fence_proxy_async();  // generic-proxy stores -> visible to the tensor core's async-proxy reads
@@ -409,6 +425,18 @@ __global__ void __launch_bounds__(kThreads, 1)
     uint32_t gbest_d[kQTilesPerCta / 2], gbest_k[kQTilesPerCta / 2];
 #pragma unroll
     for (int j = 0; j < kQTilesPerCta / 2; ++j) gbest_d[j] = 0xffffffffu, gbest_k[j] = 0u;
+#if LC_FX_ZERO_ONE_TRAIN
+    int qpop[kQTilesPerCta / 2];  // popc of this thread's queries: hamming = popc(q) - D
+#pragma unroll
+    for (int j = 0; j < kQTilesPerCta / 2; ++j) {
+      const int q = (2 * j + half) * kQTile + row;
+      qpop[j] = 0;
+      if (q < nq_blk) {
+        const uint4 a = __ldg(fr.q + 2 * (size_t)(ab.q0 + q)), b = __ldg(fr.q + 2 * (size_t)(ab.q0 + q) + 1);
+        qpop[j] = __popc(a.x) + __popc(a.y) + __popc(a.z) + __popc(a.w) + __popc(b.x) + __popc(b.y) + __popc(b.z) + __popc(b.w);
+      }
+    }
+#endif
     for (int k = k0 + slot; k < k0 + kc; k += n_slots) {
       const KfEntry kf = kfs[k];
       if (!kf_eligible(fr.cur_id, kf.frame_id, kb) || kf.n <= 0) continue;
@@ -440,8 +468,12 @@ __global__ void __launch_bounds__(kThreads, 1)
         const int m = 2 * j + half, q = m * kQTile + row;
         if (m < m_tiles && q < nq_blk) {
           const float mine = half ? best[2 * j + 1] : best[2 * j];  // static register indices
-          const float dot = fmaxf(mine, x[m * kQTile + row]);      // = 256 - 2 * min hamming
-          const uint32_t d = (uint32_t)(256 - (int)dot) >> 1;
+          const float dot = fmaxf(mine, x[m * kQTile + row]);
+#if LC_FX_ZERO_ONE_TRAIN
+          const uint32_t d = (uint32_t)(qpop[j] - (int)dot);       // dot = popc(q) - min hamming
+#else
+          const uint32_t d = (uint32_t)(256 - (int)dot) >> 1;      // dot = 256 - 2 * min hamming
+#endif
           dst[q] = (uint16_t)d;
           if (d < gbest_d[j]) gbest_d[j] = d, gbest_k[j] = (uint32_t)k;
         }
