@@ -464,7 +464,7 @@ int run_match(lc_ctx* c, cudaStream_t st, const KfEntry* d_kfs, int n_kf, int ma
         if (best_cost < 0 || cost * 10 < best_cost * 9) best_cost = cost, q_per_cta = T * fx::kQTile;
       }
     }
-    const size_t img_bytes = want_fp4 ? (size_t)fx::kABytes : (size_t)tc::kABytes;
+    const size_t img_bytes = want_fp4 ? (size_t)fx::kAImageBytes : (size_t)tc::kABytes;
     std::vector<tc::ABlock> blocks;  // fx::ABlock has the same layout
     static_assert(sizeof(tc::ABlock) == sizeof(fx::ABlock), "ABlock layouts differ");
     std::vector<int> tiles;

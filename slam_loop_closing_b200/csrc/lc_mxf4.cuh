@@ -55,6 +55,7 @@ constexpr int kSfCol = 224;                  // TMEM columns [224, 256): scale-f
 constexpr int kATileBytes = kQTile * 128;    // 16 KiB
 constexpr int kBTileBytes = kTN * 128;       // 28 KiB
 constexpr int kABytes = kQTilesPerCta * kATileBytes;  // 128 KiB
+constexpr int kAImageBytes = kABytes + kQPerCta * 2;  // a block's image in global memory: the A tiles, then popc(q) of its queries (u16)
 constexpr int kOffB = kABytes;
 constexpr int kOffXch = kOffB + kBStages * kBTileBytes;
 constexpr int kXchBytes = 2 * kQTilesPerCta * kQTile * 4;  // [parity][tile][row] f32: the column halves meet here
@@ -126,14 +127,22 @@ __global__ void __launch_bounds__(kExpandThreads)
   const QFrame fr = frames[ab.frame];
   const int tile = blockIdx.y;
   if (tile * kQTile >= ab.nq) return;  // a small block: its last tiles do not exist
-  uint8_t* img = img_base + (size_t)blockIdx.x * kABytes + (size_t)tile * kATileBytes;
+  uint8_t* block_img = img_base + (size_t)blockIdx.x * kAImageBytes;
+  uint8_t* img = block_img + (size_t)tile * kATileBytes;
+  uint16_t* qpop = reinterpret_cast<uint16_t*>(block_img + kABytes) + tile * kQTile;
   for (int idx = threadIdx.x; idx < kQTile * 8; idx += kExpandThreads) {
     const int r = idx >> 3, w = idx & 7, q = ab.q0 + tile * kQTile + r;
     // rows past the end of the block: E2M1 0.0 everywhere - their products are exact zeros that cost the tensor pipe no
     // switching power (their accumulator rows are never read)
     const bool valid = tile * kQTile + r < ab.nq;
-    const uint4 e = valid ? expand_word_fp4<true>(__ldg(reinterpret_cast<const uint32_t*>(fr.q) + (size_t)q * 8 + w)) : make_uint4(0u, 0u, 0u, 0u);
-    *reinterpret_cast<uint4*>(img + tile_offset(r, w)) = e;
+    const uint32_t bits = valid ? __ldg(reinterpret_cast<const uint32_t*>(fr.q) + (size_t)q * 8 + w) : 0u;
+    *reinterpret_cast<uint4*>(img + tile_offset(r, w)) = valid ? expand_word_fp4<true>(bits) : make_uint4(0u, 0u, 0u, 0u);
+    // popc(q) of the row: its eight words sit in eight neighbouring lanes
+    int pc = __popc(bits);
+    pc += __shfl_xor_sync(0xffffffffu, pc, 1);
+    pc += __shfl_xor_sync(0xffffffffu, pc, 2);
+    pc += __shfl_xor_sync(0xffffffffu, pc, 4);
+    if (w == 0) qpop[r] = (uint16_t)pc;
   }
   if (fill_best && fr.best_packed && threadIdx.x < kQTile) {
     const int q = ab.q0 + tile * kQTile + threadIdx.x;
@@ -426,15 +435,11 @@ __global__ void __launch_bounds__(kThreads, 1)
 #pragma unroll
     for (int j = 0; j < kQTilesPerCta / 2; ++j) gbest_d[j] = 0xffffffffu, gbest_k[j] = 0u;
 #if LC_FX_ZERO_ONE_TRAIN
-    int qpop[kQTilesPerCta / 2];  // popc of this thread's queries: hamming = popc(q) - D
+    int qpop[kQTilesPerCta / 2];  // popc of this thread's queries (expand_queries_fp4_kernel left them behind the A tiles): hamming = popc(q) - D
+    {
+      const uint16_t* pops = reinterpret_cast<const uint16_t*>(ab.img + kABytes);
 #pragma unroll
-    for (int j = 0; j < kQTilesPerCta / 2; ++j) {
-      const int q = (2 * j + half) * kQTile + row;
-      qpop[j] = 0;
-      if (q < nq_blk) {
-        const uint4 a = __ldg(fr.q + 2 * (size_t)(ab.q0 + q)), b = __ldg(fr.q + 2 * (size_t)(ab.q0 + q) + 1);
-        qpop[j] = __popc(a.x) + __popc(a.y) + __popc(a.z) + __popc(a.w) + __popc(b.x) + __popc(b.y) + __popc(b.z) + __popc(b.w);
-      }
+      for (int j = 0; j < kQTilesPerCta / 2; ++j) qpop[j] = (int)__ldg(pops + (2 * j + half) * kQTile + row);
     }
 #endif
     for (int k = k0 + slot; k < k0 + kc; k += n_slots) {
