@@ -49,6 +49,8 @@ TRAFFIC_BYTES_PER_KF = 68_900
 WORKLOADS = {
     "c4": dict(keyframes=100_000, name="C4: 2000-descriptor query vs 100k-keyframe DB (200M rows x 256 bit, 6.4 GB)"),
     "c3": dict(keyframes=1_000, name="C3: 2000-descriptor query vs 1k-keyframe DB (2M rows, 64 MB)"),
+    # BASELINE config 5 (throughput mode): one step = ONE batched check of 64 query frames (25.6 Tpairs)
+    "c5": dict(keyframes=100_000, frames=64, name="C5: batched loop check, 64 query frames x 2000 descriptors vs 100k-keyframe DB (200M rows, 6.4 GB)"),
 }
 
 
@@ -58,8 +60,9 @@ def workload_config(args, world):
     wl = WORKLOADS[args.workload]
     n_kf = args.keyframes or wl["keyframes"]
     local_rows = ((n_kf + world - 1) // world) * ROWS_PER_KF  # rank 0's shard, the largest
-    return {"workload": wl["name"] if not args.keyframes else f"{n_kf}-keyframe DB x {ROWS_PER_KF} rows", "keyframes": n_kf,
-            "rows_per_keyframe": ROWS_PER_KF, "nq": NQ, "pairs_per_step": float(NQ) * ROWS_PER_KF * n_kf,
+    frames = wl.get("frames", 1)
+    return {"workload": wl["name"] if not args.keyframes else f"{frames} query frame(s) vs {n_kf}-keyframe DB x {ROWS_PER_KF} rows", "keyframes": n_kf,
+            "rows_per_keyframe": ROWS_PER_KF, "nq": NQ, "query_frames": frames, "pairs_per_step": float(frames) * NQ * ROWS_PER_KF * n_kf,
             "sharding": f"keyframe k -> rank k % {world}; one NCCL all_gather of [records | packed bests] + one merge kernel per step"
                         if world > 1 else "single GPU",
             "kernel": args.kernel,
@@ -267,20 +270,26 @@ def main():
     kernel = {"auto": lc.KERNEL_AUTO, "popc": lc.KERNEL_POPC, "csa": lc.KERNEL_CSA, "tensor": lc.KERNEL_TENSOR, "mxf4": lc.KERNEL_MXF4}[args.kernel]
     cur_id = n_kf + 29  # every keyframe is at least min_loop_gap back
     q = query_rows()
+    F = wl.get("frames", 1)
+    import datagen
+    qs = [q] + [datagen.uniform(NQ, 7000 + i) for i in range(F - 1)]  # frame 0 is the query of the single-frame workloads
     db = ShardedLoopDB(device=local, loop_threshold=0.15, kernel=kernel, timing=1)  # every check event-timed (match_ms feeds the roofline)
     ctx = db.shard.ctx
-    q_dev = db.shard.to_device(q)
+    q_dev_all = torch.from_numpy(np.concatenate(qs)).to(device)
+    q_dev = q_dev_all[:NQ]
     torch.cuda.synchronize()
     plant_at = n_kf // 3
     perm = build_db(db, torch, n_kf, rank, world, device, plant_at, q_dev)
     sizes = ctx.db_size()
-    pairs_per_step = float(NQ) * sizes["rows"]
-    nq_arr, cur_arr = np.array([NQ], np.int32), np.array([cur_id], np.int32)
+    pairs_per_step = float(F) * NQ * sizes["rows"]
+    nq_arr, cur_arr = np.full(F, NQ, np.int32), np.full(F, cur_id, np.int32)
 
     # ---- correctness gate at full size (size-independent properties; outside the timed region)
-    rec, best = db.loop_check([q], [cur_id])
+    rec, best = db.loop_check(qs, [cur_id] * F)
     problems = []
     r = rec[0]
+    if F > 1 and not all((rec[f]["n_good"] >= 0).all() and rec[f][plant_at]["min_dist"] > 0 for f in range(1, F)):
+        problems.append("records of the other query frames malformed")
     if not (len(r) == n_kf and (r["n_good"] >= 0).all() and (r["frame_id"] == np.arange(n_kf)).all()):
         problems.append("records malformed")
     if not (r[plant_at]["min_dist"] == 0 and r[plant_at]["n_good"] == NQ):
@@ -301,7 +310,7 @@ def main():
 
     # ---- device-resident arm ("value")
     def step_device():
-        return db.merged_device(q_dev, nq_arr, cur_arr)
+        return db.merged_device(q_dev_all, nq_arr, cur_arr)
 
     for _ in range(args.warmup):
         step_device()
@@ -321,8 +330,8 @@ def main():
         # ---- end-to-end arm: host query in, host records + best out, every step
         def step_e2e():
             if world == 1:
-                return ctx.loop_check(q, cur_id, want_best=True)
-            return db.loop_check([q], [cur_id])
+                return ctx.loop_check(q, cur_id, want_best=True) if F == 1 else ctx.loop_check_batch(qs, [cur_id] * F)
+            return db.loop_check(qs, [cur_id] * F)
 
         step_e2e()
         barrier()
@@ -346,7 +355,7 @@ def main():
     #      launches of the matching kernel (lc_timing.match_ms), live, inside the e2e timed region
     if world > 1:
         for _ in range(min(3, args.steps)):
-            ctx.loop_check(q, cur_id, want_best=True)
+            ctx.loop_check(q, cur_id, want_best=True) if F == 1 else ctx.loop_check_batch(qs, [cur_id] * F)
             tm = ctx.last_timing()
             kernel_ms.append(tm.kernel_ms)
             match_ms.append(tm.match_ms)
@@ -366,7 +375,7 @@ def main():
     pairs_per_gpu = pairs_per_step / world
     kernel_names = {1: "lc::kf_scan_kernel", 2: "lc::split_kernel", 3: "lc::tc::tensor_match_kernel", 4: "lc::fx::mxf4_match_kernel"}
     hbm_peak = float(pk.get("hbm_gbs", 6650.0))
-    algo_bytes = sizes["local_rows"] * 32 + NQ * 32 + sizes["local_keyframes"] * (16 + 2 * NQ) + NQ * 8
+    algo_bytes = sizes["local_rows"] * 32 + F * (NQ * 32 + sizes["local_keyframes"] * (16 + 2 * NQ) + NQ * 8)
     hbm = {"achieved": algo_bytes / (k_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
            "frac": algo_bytes / (k_ms * 1e-3) / 1e9 / hbm_peak, "algorithmic_bytes": algo_bytes,
            "peak_source": "measured" if pk else "fallback"}
@@ -383,7 +392,7 @@ def main():
         mac_clk = 16384 if timing.path == 4 else 8192
         roof = {
             "bound": "tensor", "achieved": ach, "peak": ratio * bf16, "unit": "TFLOP/s", "frac": ach / (ratio * bf16),
-            "traffic": TRAFFIC_BYTES_PER_KF * sizes["local_keyframes"] / match_launches,
+            "traffic": TRAFFIC_BYTES_PER_KF * sizes["local_keyframes"] / match_launches if F == 1 else None,  # measured for the single-frame check only
             "kernel": kernel_names[timing.path], "path": "tcgen05 mxf4 GEMM + max, best row resolved afterwards" if timing.path == 4 else "tcgen05 int8 GEMM + arg-max",
             "ms_per_launch": m_ms / match_launches, "launches_per_step": match_launches,
             "algorithmic_flop_per_launch": pairs_per_gpu * 512 / match_launches,
@@ -416,15 +425,16 @@ def main():
         "scaling": "strong", "vs_baseline": None, "dtype": {4: "fp4", 3: "s8"}.get(timing.path, "u32"), "data": "synthetic",
         "config": workload_config(args, world),
         "e2e": {"value": pairs_per_step * args.steps / (e2e_ms * 1e-3) / 1e9, "unit": "Gpairs/s", "ms_per_step": e2e_ms / args.steps,
-                "h2d_bytes_per_step": NQ * 32, "d2h_bytes_per_step": int(n_kf * 16 + NQ * 8) if world == 1 else int((n_kf + world) * 16 + NQ * 8),
-                "api": "lc_loop_check (C ABI, host buffers)" if world == 1 else "ShardedLoopDB.loop_check (host buffers, NCCL merge)"},
+                "h2d_bytes_per_step": F * NQ * 32,
+                "d2h_bytes_per_step": F * (int(n_kf * 16 + NQ * 8) if world == 1 else int((n_kf + world) * 16 + NQ * 8)),
+                "api": ("lc_loop_check (C ABI, host buffers)" if F == 1 else "lc_loop_check_batch (C ABI, host buffers)") if world == 1
+                       else "ShardedLoopDB.loop_check (host buffers, NCCL merge)"},
         "gpu_launches": int(gpu_launches), "clocks": clocks, "roofline": roof,
         "parity": "full-size gate passed: planted-copy record, merged per-query best, sampled keyframes vs CPU oracle",
     }
-    if world == 1 and not args.no_extra:
+    if world == 1 and not args.no_extra and F == 1:
         line["extra"] = extras(lc, torch, q, kernel)
         if n_kf >= 1000:  # BASELINE config 5 in shape, on this GPU's resident DB: 64 query frames in one batched check
-            import datagen
             frames = [q] + [datagen.uniform(NQ, 7000 + i) for i in range(63)]
             ctx.loop_check_batch(frames, [cur_id] * 64)  # first call of this shape: result buffers (102 MB pinned) grow
             t0 = time.perf_counter()
