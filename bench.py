@@ -331,7 +331,7 @@ def main():
         def step_e2e():
             if world == 1:
                 return ctx.loop_check(q, cur_id, want_best=True) if F == 1 else ctx.loop_check_batch(qs, [cur_id] * F)
-            return db.loop_check(qs, [cur_id] * F)
+            return db.loop_check(qs, [cur_id] * F, copy=False)  # results read where the download left them (pinned host memory)
 
         step_e2e()
         barrier()
@@ -360,6 +360,8 @@ def main():
             kernel_ms.append(tm.kernel_ms)
             match_ms.append(tm.match_ms)
             match_launches = max(1, tm.match_launches)
+    # the FP4 tensor pipe's own peak on this GPU, now: a pure tcgen05.mma kind::mxf4 issue loop (lc_probe_mxf4_peak)
+    pipe_macs, pipe_mhz = ctx.probe_mxf4_peak(200)
     k_ms = max_over_ranks(float(np.mean(kernel_ms)))
     m_ms = max_over_ranks(float(np.mean(match_ms)))
     timing = ctx.last_timing()
@@ -400,6 +402,10 @@ def main():
                            f"of {'measured' if pk else 'fallback'}",
             "frac_of_sustained": ach / (ratio * bf16_sus),
             "nominal": {"peak": 2250.0 * ratio, "frac": ach / (2250.0 * ratio)},
+            "pipe_peak_measured": {"peak": pipe_macs * 2 / 1e12, "unit": "TFLOP/s", "frac": ach / (pipe_macs * 2 / 1e12), "sm_mhz_held": pipe_mhz,
+                                   "how": "lc_probe_mxf4_peak in this run, after the timed region: 200 ms of nothing but tcgen05.mma kind::mxf4 "
+                                          "(M128 N256 K64, operands in shared memory) on every SM; the clock is cycle counter / elapsed time"}
+                                  if timing.path == 4 else None,
             "pipe": {"pairs_per_clk_per_sm": pairs_s / n_sm / ((clocks.get("sm_mhz") or sm_max) * 1e6),
                      "peak_pairs_per_clk_per_sm": mac_clk / 256, "at_sm_mhz": clocks.get("sm_mhz") or sm_max},
             "traffic_source": "ncu dram__bytes_read.sum + dram__bytes_write.sum per keyframe of one --set full capture "

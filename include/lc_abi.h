@@ -309,6 +309,13 @@ int32_t lc_l2_loop_check(lc_ctx* ctx, const void* q, int32_t nq, size_t q_stride
                          int32_t current_frame_id, int32_t loop_gap, double ratio, int32_t min_rows,
                          lc_l2_result* results, int64_t results_cap, int64_t* n_results);
 
+/* ---- measurement aid: the peak of the pipe the default loop-check kernel runs on.  For about `milliseconds` every SM
+ *      issues nothing but tcgen05.mma kind::mxf4 (M 128 x N 256 x K 64, operands in shared memory, the match kernel's
+ *      value distribution); *mac_per_s = multiply-accumulates per second of the whole GPU (a descriptor pair is 256 of
+ *      them), *sm_mhz = the SM clock the pipe really held (cycle counter / elapsed time).  bench.py's roofline divides
+ *      by this figure, measured in the same run. ---- */
+int32_t lc_probe_mxf4_peak(lc_ctx* ctx, int32_t milliseconds, double* mac_per_s, double* sm_mhz);
+
 /* ---- introspection ---- */
 int32_t lc_get_last_timing(const lc_ctx* ctx, lc_timing* out);
 /* Number of kernels this context has launched since creation (bench.py's gpu_launches). */

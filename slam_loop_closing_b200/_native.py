@@ -85,6 +85,7 @@ SYMBOLS = {
     "lc_loop_check_batch_device": (_i32, [_vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp]),
     "lc_merge_shards_device": (_i32, [_vp, _vp, _i64, _i32, _i32, _i64, _i64, _vp, _vp, _vp]),
     "lc_match_pair_device": (_i32, [_vp, _vp, _i32, _vp, _i32, _vp, _vp, _vp, _vp, _vp]),
+    "lc_probe_mxf4_peak": (_i32, [_vp, _i32, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "lc_get_last_timing": (_i32, [_vp, C.POINTER(Timing)]),
     "lc_launch_count": (_i64, [_vp]),
     "lc_synchronize": (_i32, [_vp]),
@@ -468,6 +469,12 @@ class Context:
         self._ck(self._lib.lc_match_pair_device(self._h, d_q, int(nq), d_t, int(nt), d_idx, d_dist, d_good, d_summary, stream))
 
     # ---- introspection
+    def probe_mxf4_peak(self, milliseconds=100):
+        """(MAC/s of the whole GPU, SM MHz held) of a pure tcgen05.mma kind::mxf4 issue loop: the tensor roofline's denominator."""
+        macs, mhz = C.c_double(), C.c_double()
+        self._ck(self._lib.lc_probe_mxf4_peak(self._h, int(milliseconds), C.byref(macs), C.byref(mhz)))
+        return macs.value, mhz.value
+
     def last_timing(self) -> Timing:
         t = Timing()
         self._ck(self._lib.lc_get_last_timing(self._h, C.byref(t)))

@@ -2022,6 +2022,39 @@ LC_API int32_t lc_l2_loop_check(lc_ctx* c, const void* q, int32_t nq, size_t qs,
   LC_GUARD_END(c)
 }
 
+// ------------------------------------------------------------------- the FP4 pipe's measured peak
+LC_API int32_t lc_probe_mxf4_peak(lc_ctx* c, int32_t milliseconds, double* mac_per_s, double* sm_mhz) {
+  if (!c) return LC_ERR_INVALID;
+  LC_GUARD_BEGIN
+  if (milliseconds < 1 || milliseconds > 2000) return fail(c, LC_ERR_INVALID, "milliseconds = %d outside [1, 2000]", milliseconds);
+  LC_TRY(enter_host(c));
+  LC_TRY(ensure(c, c->d_counter, (size_t)c->num_sms * sizeof(long long)));
+  LC_CUDA(c, cudaFuncSetAttribute(fx::mxf4_peak_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, fx::kPeakSmem));
+  cudaEvent_t e0 = c->ev[0], e1 = c->ev[1];
+  double ms_run = 0.0, cyc = 0.0;
+  long long iters = 2000;  // ~0.6 ms; the second run is sized from the first
+  for (int pass = 0; pass < 2; ++pass) {
+    LC_CUDA(c, cudaEventRecord(e0, c->stream));
+    fx::mxf4_peak_kernel<<<c->num_sms, 128, fx::kPeakSmem, c->stream>>>(iters, (long long*)c->d_counter.p);
+    LC_CUDA(c, cudaGetLastError());
+    LC_CUDA(c, cudaEventRecord(e1, c->stream));
+    LC_CUDA(c, cudaStreamSynchronize(c->stream));
+    c->launches += 1;
+    float ms = 0.f;
+    LC_CUDA(c, cudaEventElapsedTime(&ms, e0, e1));
+    ms_run = ms;
+    if (pass == 0) iters = std::max<long long>(2000, (long long)((double)iters * milliseconds / std::max(ms, 0.05f)));
+  }
+  std::vector<long long> cycles((size_t)c->num_sms);
+  LC_CUDA(c, cudaMemcpy(cycles.data(), c->d_counter.p, cycles.size() * sizeof(long long), cudaMemcpyDeviceToHost));
+  for (long long v : cycles) cyc = std::max(cyc, (double)v);
+  const double macs = (double)c->num_sms * (double)iters * 4.0 * fx::kQTile * fx::kPeakN * 64.0;
+  if (mac_per_s) *mac_per_s = macs / (ms_run * 1e-3);
+  if (sm_mhz) *sm_mhz = cyc / (ms_run * 1e-3) / 1e6;
+  return LC_OK;
+  LC_GUARD_END(c)
+}
+
 // ------------------------------------------------------------------- introspection
 LC_API int32_t lc_get_last_timing(const lc_ctx* c, lc_timing* out) {
   if (!c || !out) return LC_ERR_INVALID;

@@ -502,6 +502,66 @@ __global__ void __launch_bounds__(kThreads, 1)
   }
 }
 
+// ---------------------------------------------------------------- the pipe's measured peak (roofline denominator)
+// One CTA per SM issues `iters` x 4 kind::mxf4 MMAs (M = 128, N = 256, K = 64, operands in shared memory with the match
+// kernel's value distribution: A = -1 / +1, B = 0 / +1) back to back into one accumulator and waits for the last one:
+// nothing but the tensor pipe.  MACs / elapsed time is what bench.py divides the match kernel's rate by, and
+// cycles / elapsed time is the SM clock the pipe really ran at.
+constexpr int kPeakN = 256;
+constexpr int kPeakSmem = kATileBytes + kPeakN * 128 + 1024;
+__global__ void __launch_bounds__(128, 1) mxf4_peak_kernel(long long iters, long long* cycles_out) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tmem_slot;
+  uint32_t rng = 0x9e3779b9u * (blockIdx.x * 128 + threadIdx.x + 1);
+  for (int i = threadIdx.x; i < (kATileBytes + kPeakN * 128) / 16; i += blockDim.x) {
+    rng = rng * 1664525u + 1013904223u;
+    const uint32_t bits = rng >> 8;
+    reinterpret_cast<uint4*>(smem)[i] = i < kATileBytes / 16 ? expand_word_fp4<true>(bits) : expand_word_fp4<false>(bits);
+  }
+  if (threadIdx.x == 0) {
+    if (smem_u32(smem) & 1023u) __trap();
+    mbar_init(&bar, 1);
+    mbar_fence_init();
+  }
+  const int warp = threadIdx.x >> 5;
+  if (warp == 0) tc::tmem_alloc(&tmem_slot, kTmemCols);
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_slot;
+  for (int c = 0; c < 64; ++c) tmem_st1(tmem_base + ((uint32_t)(warp * 32) << 16) + kPeakN + c, 0x7f7f7f7fu);  // scales = 1.0
+  tmem_st_wait();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (warp == 0) {
+    const uint32_t idesc = instr_desc_mxf4(kPeakN);
+    const uint64_t adesc = tc::smem_desc(smem_u32(smem)), bdesc = tc::smem_desc(smem_u32(smem) + kATileBytes);
+    const bool leader = elect_one();
+    const long long t0 = clock64();
+    for (long long it = 0; it < iters; ++it) {
+      if (leader) {
+#pragma unroll
+        for (int s = 0; s < 4; ++s)
+          umma_mxf4(tmem_base, adesc + (uint64_t)(s * 2), bdesc + (uint64_t)(s * 2), idesc, (it | s) ? 1u : 0u, tmem_base + kPeakN, tmem_base + kPeakN + 32);
+      }
+      __syncwarp();
+    }
+    if (leader) umma_commit_a(smem_u32(&bar));
+    __syncwarp();
+    while (!mbar_try_a(smem_u32(&bar), 0)) {}
+    if (threadIdx.x == 0) cycles_out[blockIdx.x] = clock64() - t0;
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tc::tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
 // ---------------------------------------------------------------- finalize (distance-only scratch)
 // one WARP per (frame, keyframe in [k0, k0 + kc)): min distance, 2 x min filter, count -> results[frame * n_kf + k].
 // The 16-bit distances of one match (<= 4 KiB) are read once with 128-bit loads and stay in registers for both passes.

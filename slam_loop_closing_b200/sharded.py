@@ -130,10 +130,11 @@ class ShardedLoopDB:
         self.n_keyframes += 1
         return k
 
-    def loop_check(self, queries, current_frame_ids):
+    def loop_check(self, queries, current_frame_ids, copy=True):
         """queries: list of (nq,32) uint8 arrays (or one CUDA uint8 tensor of concatenated rows with
         `nq` given via a tuple (tensor, nq_list)).  Returns (records [F][K] KF_RESULT in global keyframe
-        order, best list of uint64 arrays)."""
+        order, best list of uint64 arrays).  copy=False: the arrays are views of the pinned download buffers (two sets,
+        used in turn), valid until the next-but-one call - no second pass over 16 bytes per (frame, keyframe)."""
         if isinstance(queries, tuple):
             d_q, nq = queries
             nq = np.asarray(nq, np.int32)
@@ -147,20 +148,28 @@ class ShardedLoopDB:
         K = self.n_keyframes
         rec_h, best_h = self._to_host(rec.reshape(-1), best)  # both downloads queued, one synchronisation
         # a merged record is four int32 in lc_kf_result order: reinterpret instead of copying field by field
-        out = rec_h.view(np.int32).reshape(len(nq), -1, 4)[:, :K].copy().view(_native.KF_RESULT).reshape(len(nq), K)
+        out = rec_h.view(np.int32).reshape(len(nq), -1, 4)[:, :K]
+        out = (out.copy() if copy else np.ascontiguousarray(out)).view(_native.KF_RESULT).reshape(len(nq), K)
         b = best_h.view(np.uint64)
         offs = np.concatenate([[0], np.cumsum(nq)])
-        return out, [b[offs[i]:offs[i + 1]].copy() for i in range(len(nq))]
+        return out, [b[offs[i]:offs[i + 1]].copy() if copy else b[offs[i]:offs[i + 1]] for i in range(len(nq))]
 
     def _to_host(self, rec_flat, best):
-        """Device results -> numpy through pinned staging (CUDA tensors) or directly (the CPU test double)."""
+        """Device results -> numpy through pinned staging (CUDA tensors) or directly (the CPU test double).  Two staging
+        sets take turns, so that what the previous call returned (copy=False) survives this one."""
         if not rec_flat.is_cuda:
             return rec_flat.numpy(), best.numpy()
         need = (rec_flat.numel(), best.numel())
-        if getattr(self, "_pin_out", None) is None or self._pin_out[0].numel() < need[0] or self._pin_out[1].numel() < need[1]:
-            self._pin_out = (torch.empty(max(need[0], 1), dtype=torch.int32).pin_memory(),
-                             torch.empty(max(need[1], 1), dtype=torch.int64).pin_memory())
-        r, b = self._pin_out[0][:need[0]], self._pin_out[1][:need[1]]
+        pool = getattr(self, "_pin_pool", None)
+        if pool is None:
+            pool = self._pin_pool = [None, None]
+            self._pin_turn = 0
+        self._pin_turn ^= 1
+        cur = pool[self._pin_turn]
+        if cur is None or cur[0].numel() < need[0] or cur[1].numel() < need[1]:
+            cur = pool[self._pin_turn] = (torch.empty(max(need[0], 1), dtype=torch.int32).pin_memory(),
+                                          torch.empty(max(need[1], 1), dtype=torch.int64).pin_memory())
+        r, b = cur[0][:need[0]], cur[1][:need[1]]
         r.copy_(rec_flat, non_blocking=True)
         b.copy_(best, non_blocking=True)
         torch.cuda.current_stream(rec_flat.device).synchronize()

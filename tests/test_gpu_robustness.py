@@ -251,3 +251,14 @@ def test_timing_of_a_pending_check_survives_calls_made_meanwhile(lc):
         # and an ordinary call afterwards is timed again
         c.match_pair(a, b)
         assert c.last_timing().total_ms > 0
+
+
+def test_mxf4_peak_probe_reports_a_plausible_pipe_rate(lc):
+    """lc_probe_mxf4_peak: the roofline denominator bench.py measures live - 16384 MAC/clk/SM x 148 SMs at 1.5-1.97 GHz."""
+    with lc.Context() as c:
+        macs, mhz = c.probe_mxf4_peak(30)
+        assert 1400 < mhz < 2000, mhz
+        per_clk_per_sm = macs / (mhz * 1e6) / 148
+        assert 15000 < per_clk_per_sm < 16500, per_clk_per_sm
+        with pytest.raises(lc.LcError):
+            c.probe_mxf4_peak(0)
