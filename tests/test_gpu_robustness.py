@@ -262,3 +262,23 @@ def test_mxf4_peak_probe_reports_a_plausible_pipe_rate(lc):
         assert 15000 < per_clk_per_sm < 16500, per_clk_per_sm
         with pytest.raises(lc.LcError):
             c.probe_mxf4_peak(0)
+
+
+def test_sharded_db_results_as_views_survive_one_more_call(lc):
+    """ShardedLoopDB.loop_check(copy=False): records and bests are views of two pinned download buffers used in turn."""
+    from slam_loop_closing_b200.sharded import ShardedLoopDB
+    p = Params(loop_threshold=0.15, min_loop_gap=0)
+    q1, q2 = datagen.uniform(700, 1), datagen.low_entropy(650, 2)
+    kfs = datagen.structured_db(q1, 90, n=300, every=4, ragged=True)
+    fids = list(range(90))
+    rows, ns = np.concatenate(kfs), [len(k) for k in kfs]
+    db = ShardedLoopDB(device=0, loop_threshold=0.15, min_loop_gap=0)
+    for fid, kf in zip(fids, kfs):
+        db.append(fid, kf)
+    rec_a, best_a = db.loop_check([q1], [200], copy=False)
+    rec_b, best_b = db.loop_check([q2], [200], copy=False)
+    for (rec, best), q in (((rec_a, best_a), q1), ((rec_b, best_b), q2)):
+        w_res, w_best = c_oracle.loop_check(q, rows, ns, fids, 200, p, nthreads=8)
+        np.testing.assert_array_equal(rec[0], w_res)
+        np.testing.assert_array_equal(best[0], w_best)
+    db.shard.ctx.close()

@@ -122,6 +122,14 @@ def test_world_one_needs_no_process_group():
     want_res, want_best = c_oracle.loop_check(qs[0], np.concatenate(kfs), [len(k) for k in kfs], fids, curs[0], p)
     np.testing.assert_array_equal(rec[0], want_res)
     np.testing.assert_array_equal(best[0], want_best)
+    # copy=False hands out views of the download buffers: what one call returned survives the next call
+    rec_a, best_a = db.loop_check(qs[:1], curs[:1], copy=False)
+    rec_b, best_b = db.loop_check(qs[1:2], curs[1:2], copy=False)
+    np.testing.assert_array_equal(rec_a[0], want_res)
+    np.testing.assert_array_equal(best_a[0], want_best)
+    w2 = c_oracle.loop_check(qs[1], np.concatenate(kfs), [len(k) for k in kfs], fids, curs[1], p)
+    np.testing.assert_array_equal(rec_b[0], w2[0])
+    np.testing.assert_array_equal(best_b[0], w2[1])
 
 
 @pytest.mark.parametrize("world,F,slots,rows", [(1, 1, 5, 7), (2, 1, 3, 0), (3, 2, 4, 11), (8, 3, 1, 5), (4, 1, 0, 3)])
