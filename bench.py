@@ -41,10 +41,10 @@ QUERY_SEED, DB_SEED = 1234, 5678
 CHUNK_KF = 2500  # keyframes generated per device chunk (160 MB)
 POPC_PER_CLK_PER_SM = 16  # measured: profiles/r01_pipe_rates_b200.json (15.1 sustained in a pure-POPC loop)
 POPC_PER_PAIR = 8
-# ncu --set full, lc::fx::mxf4_match_kernel on 4000 keyframes x 2000 rows (profiles/r01_ncu_mxf4_match.txt: 256.6 MB read,
-# 17.7 MB written):
+# ncu --set full, lc::fx::mxf4_match_kernel on 4000 keyframes x 2000 rows (profiles/r02_ncu_mxf4_match.txt: 256.4 MB read,
+# 16.2 MB written):
 # dram read + write bytes per keyframe (64,000 B of rows are the algorithmic read; 4,000 B of u16 distances the write)
-TRAFFIC_BYTES_PER_KF = 68_900
+TRAFFIC_BYTES_PER_KF = 68_165
 
 WORKLOADS = {
     "c4": dict(keyframes=100_000, name="C4: 2000-descriptor query vs 100k-keyframe DB (200M rows x 256 bit, 6.4 GB)"),
