@@ -160,7 +160,10 @@ def cpu_baseline(q, budget_s=12.0):
     dt, pairs, kind = cpu_loop_check_sample(q, 8, threads)  # probe (also warms cv2's thread pool)
     n = int(max(16, min(4000, budget_s / (dt / 8))))
     dt, pairs, kind = cpu_loop_check_sample(q, n, threads)
+    n1 = int(max(8, min(200, n // (4 * max(threads // 2, 1)))))  # the same at cv::setNumThreads(1), ~3 s
+    dt1, pairs1, _ = cpu_loop_check_sample(q, n1, 1)
     return {"value": pairs / dt / 1e9, "unit": "Gpairs/s", "cores": threads, "kind": "port",
+            "single_thread": {"value": pairs1 / dt1 / 1e9, "unit": "Gpairs/s", "cores": 1, "sample": f"{n1} keyframes, cv2.setNumThreads(1)"},
             "sample": f"{n} keyframes x {ROWS_PER_KF} rows vs the {NQ}-row query ({pairs / 1e9:.1f} Gpairs, {dt:.1f} s): {kind}; "
                       f"the reference's own loop_closing.cpp is absent, this is the OpenCV call its matcher_ makes",
             "ms_per_keyframe": dt / n * 1e3}
