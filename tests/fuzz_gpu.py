@@ -67,6 +67,37 @@ def _one_case(rng, cases):
                 assert np.array_equal(g["train_idx"], w["train_idx"]) and np.array_equal(g["dist"], w["dist"]) and \
                     np.array_equal(g["good"].astype(bool), w["good"]) and (g["min_dist"], g["n_good"]) == (w["min_dist"], w["n_good"]), \
                     (cases, "pair", a.shape, b.shape)
+        if cases % 3 == 0:  # lc_process_frame: a short random frame sequence, fused call == the oracle frame by frame
+            pf = Params(loop_threshold=float(rng.choice([0.05, 0.15, 0.5])), min_loop_gap=int(rng.integers(0, 6)), filter_floor=int(rng.choice([0, 30])),
+                        gap_strict=bool(rng.integers(0, 2)), thr_inclusive=bool(rng.integers(0, 2)))
+            n_fr, hi = int(rng.integers(2, 14)), int(rng.choice([60, 900, 2300]))
+            seq = []
+            for i in range(n_fr):
+                n = int(rng.integers(0, hi))
+                full = [x for x in seq if len(x)]
+                if full and n and rng.integers(0, 2):  # a revisit: a noisy copy of an earlier frame
+                    seq.append(datagen.noisy_copy(full[int(rng.integers(0, len(full)))], int(rng.integers(1 << 30)), p=0.05, n=n))
+                else:
+                    seq.append(gen(n, int(rng.integers(1 << 30))))
+            with lc.Context(kernel=int(rng.choice([0, 2, 4])), loop_threshold=pf.loop_threshold, min_loop_gap=pf.min_loop_gap, filter_floor=pf.filter_floor,
+                            gap_strict=pf.gap_strict, thr_inclusive=pf.thr_inclusive) as c:
+                for i, d in enumerate(seq):
+                    if rng.integers(0, 2):
+                        pair, cands, k = c.process_frame(3 * i, d)
+                    else:
+                        k = c.process_frame_begin(3 * i, d)
+                        pair, cands = c.process_frame_matches(), c.process_frame_end()
+                    assert k == i
+                    if i:
+                        w = c_oracle.match_features(seq[i - 1], d, pf, nthreads=16)
+                        assert np.array_equal(pair["train_idx"], w["train_idx"]) and np.array_equal(pair["dist"], w["dist"]) and \
+                            np.array_equal(pair["good"].astype(bool), w["good"]) and (pair["min_dist"], pair["n_good"]) == (w["min_dist"], w["n_good"]), \
+                            (cases, "frame pair", i)
+                    w_res, _ = c_oracle.loop_check(d, np.concatenate(seq[:i + 1]), [len(x) for x in seq[:i + 1]], [3 * j for j in range(i + 1)], 3 * i, pf,
+                                                   nthreads=16)
+                    want = c_oracle.loop_candidates(w_res, len(d), 3 * i, pf)
+                    got = [(int(x["current_frame_id"]), int(x["matched_frame_id"]), int(x["num_matches"]), float(x["similarity_score"])) for x in cands]
+                    assert got == [tuple(x) for x in want], (cases, "frame loops", i)
         if cases % 7 == 0:  # the SIFT / L2 path
             a = rng.integers(0, 256, (int(rng.integers(1, 1500)), 128)).astype(np.uint8)
             b = rng.integers(0, 256, (int(rng.integers(1, 1500)), 128)).astype(np.uint8)
