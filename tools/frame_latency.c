@@ -3,7 +3,7 @@
  *   separate: lc_match_pair(prev, cur) + lc_db_append(cur) + lc_detect_loops(cur)   (three uploads, three waits)
  *   fused:    lc_process_frame(cur)                                                 (one upload, one wait)
  * gcc -O2 -I include tools/frame_latency.c slam_loop_closing_b200/csrc/liblc_b200.so -Wl,-rpath,$PWD/slam_loop_closing_b200/csrc -o build/frame_latency
- * usage: frame_latency [frames] [rows] */
+ * usage: frame_latency [frames] [rows] [timing: 1 = also print the device-side split of the fused call (event-timed run)] */
 #define _POSIX_C_SOURCE 199309L
 #include <stdio.h>
 #include <stdlib.h>
@@ -23,7 +23,7 @@ static double median(double* v, int n) {
 }
 
 int main(int argc, char** argv) {
-  const int F = argc > 1 ? atoi(argv[1]) : 97, n = argc > 2 ? atoi(argv[2]) : 2000;
+  const int F = argc > 1 ? atoi(argv[1]) : 97, n = argc > 2 ? atoi(argv[2]) : 2000, timed = argc > 3 ? atoi(argv[3]) : 0;
   uint8_t* frames = malloc((size_t)F * n * 32);
   unsigned s = 4242u;
   for (size_t i = 0; i < (size_t)F * n * 32; ++i) frames[i] = (uint8_t)((s = s * 1664525u + 1013904223u) >> 24);
@@ -77,5 +77,29 @@ int main(int argc, char** argv) {
     }
   }
   if (loops[0] != loops[1] || good_sum[0] != good_sum[1]) { fprintf(stderr, "MISMATCH between the two modes\n"); return 2; }
+  if (timed) { /* the fused call again with CUDA events on (they cost ~20 us per call, so only the split is meaningful) */
+    lc_config cfg;
+    lc_default_config(&cfg);
+    cfg.loop_threshold = 0.15;
+    cfg.timing = LC_TIMING_ON;
+    lc_ctx* c = NULL;
+    if (lc_create(&cfg, &c) != 0) return 1;
+    double h2d = 0, ker = 0, d2h = 0, tot = 0, mk = 0;
+    int cnt = 0, launches = 0;
+    for (int f = 0; f < F; ++f) {
+      int32_t nm, md, ng;
+      int64_t n_out;
+      if (lc_process_frame(c, f, frames + (size_t)f * n * 32, n, 32, idx, dist, good, n, &nm, &md, &ng, out, F, &n_out, NULL) != 0) return 1;
+      if (f >= F - F / 3) {
+        lc_timing tm;
+        lc_get_last_timing(c, &tm);
+        h2d += tm.h2d_ms; ker += tm.kernel_ms; d2h += tm.d2h_ms; tot += tm.total_ms; mk += tm.match_ms; launches = tm.kernel_launches;
+        ++cnt;
+      }
+    }
+    printf("fused, device side (means over the last %d frames): upload + table poke %.1f us, kernels %.1f us (loop-check matching kernel %.1f us), "
+           "download %.1f us, first to last %.1f us; %d launches\n", cnt, h2d / cnt * 1e3, ker / cnt * 1e3, mk / cnt * 1e3, d2h / cnt * 1e3, tot / cnt * 1e3, launches);
+    lc_destroy(c);
+  }
   return 0;
 }
