@@ -39,6 +39,7 @@ NQ = 2000
 ROWS_PER_KF = 2000
 QUERY_SEED, DB_SEED = 1234, 5678
 CHUNK_KF = 2500  # keyframes generated per device chunk (160 MB)
+ARM_PAUSE_S = 1.0  # idle time before each arm's warm-up (see main)
 POPC_PER_CLK_PER_SM = 16  # measured: profiles/r01_pipe_rates_b200.json (15.1 sustained in a pure-POPC loop)
 POPC_PER_PAIR = 8
 # ncu --set full, lc::fx::mxf4_match_kernel on 4000 keyframes x 2000 rows (profiles/r02_ncu_mxf4_match.txt: 256.4 MB read,
@@ -66,6 +67,7 @@ def workload_config(args, world):
             "sharding": f"keyframe k -> rank k % {world}; one NCCL all_gather of [records | packed bests] + one merge kernel per step"
                         if world > 1 else "single GPU",
             "kernel": args.kernel,
+            "timing": f"each arm: {ARM_PAUSE_S:.0f} s idle, warm-up steps, then the timed steps (CUDA events, max over ranks)",
             "l2": f"inputs larger than L2: each step streams the {local_rows * 32 / 1e9:.2f} GB DB shard from HBM"}
 
 
@@ -315,6 +317,11 @@ def main():
     def step_device():
         return db.merged_device(q_dev_all, nq_arr, cur_arr)
 
+    # Both arms start from the same state: a second of idle (a B200 that has just run a second of FP4 MMAs is 1-2 % slower
+    # under its power cap than one that starts from idle - tools/arm_order_probe.py - and the arms run one after the other),
+    # then the warm-up steps, then the timed steps.
+    barrier()
+    time.sleep(ARM_PAUSE_S)
     for _ in range(args.warmup):
         step_device()
     barrier()
@@ -336,7 +343,10 @@ def main():
                 return ctx.loop_check(q, cur_id, want_best=True) if F == 1 else ctx.loop_check_batch(qs, [cur_id] * F)
             return db.loop_check(qs, [cur_id] * F, copy=False)  # results read where the download left them (pinned host memory)
 
-        step_e2e()
+        barrier()
+        time.sleep(ARM_PAUSE_S)
+        for _ in range(min(args.warmup, 3)):
+            step_e2e()
         barrier()
         kernel_ms, match_ms, match_launches = [], [], 1
         t0 = time.perf_counter()

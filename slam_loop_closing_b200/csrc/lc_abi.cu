@@ -2027,6 +2027,7 @@ LC_API int32_t lc_probe_mxf4_peak(lc_ctx* c, int32_t milliseconds, double* mac_p
   if (!c) return LC_ERR_INVALID;
   LC_GUARD_BEGIN
   if (milliseconds < 1 || milliseconds > 2000) return fail(c, LC_ERR_INVALID, "milliseconds = %d outside [1, 2000]", milliseconds);
+  if (c->pending.active) return fail(c, LC_ERR_INVALID, "a loop check or a frame is pending (its timing events are in use)");
   LC_TRY(enter_host(c));
   LC_TRY(ensure(c, c->d_counter, (size_t)c->num_sms * sizeof(long long)));
   LC_CUDA(c, cudaFuncSetAttribute(fx::mxf4_peak_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, fx::kPeakSmem));

@@ -551,7 +551,7 @@ __global__ void __launch_bounds__(128, 1) mxf4_peak_kernel(long long iters, long
     }
     if (leader) umma_commit_a(smem_u32(&bar));
     __syncwarp();
-    while (!mbar_try_a(smem_u32(&bar), 0)) {}
+    mbar_wait_a(smem_u32(&bar), 0);  // bounded: a tensor pipe that never answers traps instead of hanging the GPU
     if (threadIdx.x == 0) cycles_out[blockIdx.x] = clock64() - t0;
   }
   tc_fence_before();

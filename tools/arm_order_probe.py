@@ -47,6 +47,12 @@ for rnd in range(3):
     d = device_arm()
     e, m = e2e_arm()
     print(f"round {rnd}: device arm {d:.3f} ms/step ({pairs / d / 1e6:.0f} Gpairs/s) | e2e arm {e:.3f} ms/step, match kernels {m:.3f} ms of it", flush=True)
+for pause in (0.5, 2.0, 5.0):
+    time.sleep(pause)
+    d = device_arm()
+    time.sleep(pause)
+    e, m = e2e_arm()
+    print(f"after a {pause} s pause before each arm: device arm {d:.3f} ms/step | e2e arm {e:.3f} ms/step (match {m:.3f})", flush=True)
 ctx.set_params(timing=0)
 for rnd in range(2):
     e, m = e2e_arm()
