@@ -261,6 +261,23 @@ int32_t lc_process_frame_end(lc_ctx* ctx, lc_loop_candidate* out, int64_t out_ca
 int32_t lc_merge_shards_device(lc_ctx* ctx, const void* d_gathered, int64_t contrib_bytes, int32_t world, int32_t n_frames,
                                int64_t slots, int64_t rows, lc_kf_result* d_records_out, uint64_t* d_best_out,
                                void* cuda_stream);
+/* The same merge WITHOUT a collective, over peer memory (NVLink / NVSwitch): every rank owns an exchange buffer
+ * [flags | slot 0 | slot 1] that its peers map; a check of sequence number `seq` (1, 2, 3, ... - the same on every rank)
+ * lets lc_loop_check_batch_device write its [records | bests] contribution into slot seq & 1 of its OWN buffer
+ * (lc_exchange_slot), and ONE kernel signals the peers, waits for their signals and reads their slots directly while it
+ * merges (lc_kernels.cuh: merge_peers_kernel).  Setup, once: lc_exchange_create (slot_bytes >= the largest contribution;
+ * returns a 64-byte CUDA IPC handle and/or the buffer's device address), exchange the handles by any means (MPI,
+ * torch.distributed, a socket), lc_exchange_connect with all `world` handles in rank order - or, for ranks of ONE process
+ * with peer access enabled, with their buffers' device addresses.  phase: 3 = signal + wait + merge (the normal call);
+ * 1 = signal only, 2 = wait + merge only (for drivers that emulate several ranks on one GPU, where kernels must not wait
+ * for each other).  A peer that never signals makes the kernel trap after 5 s (an error at the next synchronisation). */
+#define LC_IPC_HANDLE_BYTES 64
+int32_t lc_exchange_create(lc_ctx* ctx, int64_t slot_bytes, void* ipc_handle_out, void** d_base_out);
+int32_t lc_exchange_connect(lc_ctx* ctx, int32_t world, int32_t rank, const void* ipc_handles, void* const* d_bases);
+int32_t lc_exchange_slot(lc_ctx* ctx, int64_t seq, void** d_slot, int64_t* slot_bytes);
+int32_t lc_exchange_close(lc_ctx* ctx);
+int32_t lc_merge_shards_peer_device(lc_ctx* ctx, int64_t seq, int32_t n_frames, int64_t slots, int64_t rows,
+                                    lc_kf_result* d_records_out, uint64_t* d_best_out, int32_t phase, void* cuda_stream);
 /* ---- device-pointer variants: everything already in HBM, asynchronous on `cuda_stream`
  *      (a cudaStream_t; NULL = the context's own non-blocking stream - pass cudaStreamLegacy (0x1) to
  *      mean the legacy default stream).  d_q: contiguous 32-byte rows, 16-byte

@@ -84,6 +84,11 @@ SYMBOLS = {
     "lc_loop_check_device": (_i32, [_vp, _vp, _i32, _i32, _vp, _vp, _vp]),
     "lc_loop_check_batch_device": (_i32, [_vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp]),
     "lc_merge_shards_device": (_i32, [_vp, _vp, _i64, _i32, _i32, _i64, _i64, _vp, _vp, _vp]),
+    "lc_exchange_create": (_i32, [_vp, _i64, _vp, C.POINTER(_vp)]),
+    "lc_exchange_connect": (_i32, [_vp, _i32, _i32, _vp, _vp]),
+    "lc_exchange_slot": (_i32, [_vp, _i64, C.POINTER(_vp), _pi64]),
+    "lc_exchange_close": (_i32, [_vp]),
+    "lc_merge_shards_peer_device": (_i32, [_vp, _i64, _i32, _i64, _i64, _vp, _vp, _i32, _vp]),
     "lc_match_pair_device": (_i32, [_vp, _vp, _i32, _vp, _i32, _vp, _vp, _vp, _vp, _vp]),
     "lc_probe_mxf4_peak": (_i32, [_vp, _i32, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "lc_get_last_timing": (_i32, [_vp, C.POINTER(Timing)]),
@@ -464,6 +469,33 @@ class Context:
     def merge_shards_device(self, d_gathered, contrib_bytes, world, n_frames, slots, rows, d_records_out, d_best_out, stream=None):
         self._ck(self._lib.lc_merge_shards_device(self._h, d_gathered, int(contrib_bytes), int(world), int(n_frames), int(slots),
                                                   int(rows), d_records_out, d_best_out, stream))
+
+    # ---- peer-memory exchange of a sharded check (no collective)
+    def exchange_create(self, slot_bytes):
+        """Returns (64-byte CUDA IPC handle, device address) of this rank's exchange buffer."""
+        handle = (C.c_ubyte * 64)()
+        base = _vp()
+        self._ck(self._lib.lc_exchange_create(self._h, int(slot_bytes), handle, C.byref(base)))
+        return bytes(handle), base.value
+
+    def exchange_connect(self, world, rank, handles=None, bases=None):
+        """handles: list of `world` 64-byte IPC handles in rank order (ranks in other processes); bases: list of device
+        addresses (ranks of this process)."""
+        h = b"".join(handles) if handles is not None else None
+        b = (C.c_void_p * world)(*bases) if bases is not None else None
+        self._ck(self._lib.lc_exchange_connect(self._h, int(world), int(rank), h, b))
+
+    def exchange_slot(self, seq):
+        p, n = _vp(), C.c_int64()
+        self._ck(self._lib.lc_exchange_slot(self._h, int(seq), C.byref(p), C.byref(n)))
+        return p.value, n.value
+
+    def exchange_close(self):
+        self._ck(self._lib.lc_exchange_close(self._h))
+
+    def merge_shards_peer_device(self, seq, n_frames, slots, rows, d_records_out, d_best_out, phase=3, stream=None):
+        self._ck(self._lib.lc_merge_shards_peer_device(self._h, int(seq), int(n_frames), int(slots), int(rows), d_records_out, d_best_out,
+                                                       int(phase), stream))
 
     def match_pair_device(self, d_q, nq, d_t, nt, d_idx, d_dist, d_good, d_summary, stream=None):
         self._ck(self._lib.lc_match_pair_device(self._h, d_q, int(nq), d_t, int(nt), d_idx, d_dist, d_good, d_summary, stream))

@@ -107,6 +107,15 @@ struct lc_ctx {
   uint8_t* pin_frame_dev = nullptr;
   size_t pin_frame_cap = 0;
   cudaEvent_t pair_ev = nullptr;     // after the pair kernel of lc_process_frame_begin
+  // peer-memory exchange of a keyframe-sharded check (lc_exchange_* / lc_merge_shards_peer_device)
+  struct Exchange {
+    uint8_t* base = nullptr;  // this rank's buffer: header (flags) + two slots
+    size_t slot_bytes = 0;
+    int world = 0, rank = 0;
+    bool connected = false;
+    uint8_t* peer[kMaxPeers] = {};
+    bool ipc[kMaxPeers] = {};  // opened with cudaIpcOpenMemHandle (to be closed)
+  } xchg;
   bool smem_attr_set = false;  // the tensor kernels' dynamic shared-memory limit has been raised on this device
   // ---- the SIFT / L2 store of the shipped pipeline's matcher (lc_l2.cuh): 128-byte rows + their squared norms
   struct L2Store {
@@ -934,6 +943,9 @@ LC_API void lc_destroy(lc_ctx* c) {
   if (!c) return;
   cudaSetDevice(c->cfg.device);
   if (c->stream) cudaStreamSynchronize(c->stream);
+  for (int r = 0; r < kMaxPeers; ++r)
+    if (c->xchg.ipc[r] && c->xchg.peer[r]) cudaIpcCloseMemHandle(c->xchg.peer[r]);
+  if (c->xchg.base) cudaFree(c->xchg.base);
   for (void* p : c->slabs) cudaFree(p);
   for (void* p : c->l2s.slabs) cudaFree(p);
   for (DevBuf* b : {&c->l2s.d_kf, &c->d_l2q, &c->d_l2t, &c->d_l2norm, &c->d_l2res, &c->d_l2frames, &c->d_l2out, &c->d_l2img, &c->d_l2tables})
@@ -1403,6 +1415,119 @@ LC_API int32_t lc_merge_shards_device(lc_ctx* c, const void* d_gathered, int64_t
   const long long items = std::max<long long>(n_rec * world, rows);
   const int grid = (int)std::min<long long>((items + 255) / 256, 8ll * c->num_sms);
   merge_shards_kernel<<<grid, 256, 0, st>>>((const uint8_t*)d_gathered, (size_t)contrib_bytes, world, n_rec, rows, (uint4*)d_records_out, d_best_out);
+  LC_CUDA(c, cudaGetLastError());
+  c->launches += 1;
+  return LC_OK;
+  LC_GUARD_END(c)
+}
+
+// ------------------------------------------------------------------- peer-memory exchange (no collective)
+namespace {
+void exchange_release(lc_ctx* c) {
+  auto& x = c->xchg;
+  for (int r = 0; r < kMaxPeers; ++r) {
+    if (x.ipc[r] && x.peer[r]) cudaIpcCloseMemHandle(x.peer[r]);
+    x.peer[r] = nullptr;
+    x.ipc[r] = false;
+  }
+  if (x.base) cudaFree(x.base);
+  x = lc_ctx::Exchange{};
+}
+}  // namespace
+
+LC_API int32_t lc_exchange_create(lc_ctx* c, int64_t slot_bytes, void* ipc_handle_out, void** d_base_out) {
+  if (!c) return LC_ERR_INVALID;
+  LC_GUARD_BEGIN
+  if (slot_bytes < 16 || slot_bytes % 16 != 0) return fail(c, LC_ERR_INVALID, "slot_bytes = %lld: a positive multiple of 16 is needed", (long long)slot_bytes);
+  LC_TRY(enter_host(c));
+  LC_CUDA(c, cudaStreamSynchronize(c->stream));
+  exchange_release(c);
+  auto& x = c->xchg;
+  void* p = nullptr;
+  LC_CUDA(c, cudaMalloc(&p, kXchgHeaderBytes + 2 * (size_t)slot_bytes));
+  x.base = (uint8_t*)p;
+  x.slot_bytes = (size_t)slot_bytes;
+  LC_CUDA(c, cudaMemset(x.base, 0, kXchgHeaderBytes));  // no rank has signalled anything: sequence numbers start at 1
+  if (ipc_handle_out) {
+    static_assert(sizeof(cudaIpcMemHandle_t) == LC_IPC_HANDLE_BYTES, "LC_IPC_HANDLE_BYTES must be the size of a CUDA IPC handle");
+    cudaIpcMemHandle_t h;
+    LC_CUDA(c, cudaIpcGetMemHandle(&h, x.base));
+    memcpy(ipc_handle_out, &h, sizeof h);
+  }
+  if (d_base_out) *d_base_out = x.base;
+  return LC_OK;
+  LC_GUARD_END(c)
+}
+
+LC_API int32_t lc_exchange_connect(lc_ctx* c, int32_t world, int32_t rank, const void* ipc_handles, void* const* d_bases) {
+  if (!c) return LC_ERR_INVALID;
+  LC_GUARD_BEGIN
+  auto& x = c->xchg;
+  if (!x.base) return fail(c, LC_ERR_INVALID, "lc_exchange_connect before lc_exchange_create");
+  if (world < 1 || world > kMaxPeers || rank < 0 || rank >= world) return fail(c, LC_ERR_INVALID, "world %d / rank %d (at most %d ranks)", world, rank, kMaxPeers);
+  if (world > 1 && !ipc_handles && !d_bases) return fail(c, LC_ERR_INVALID, "neither IPC handles nor mapped base pointers given");
+  LC_TRY(enter_host(c));
+  for (int r = 0; r < world; ++r) {
+    if (r == rank) {
+      x.peer[r] = x.base;
+    } else if (d_bases) {  // peers of the same process (their buffers are already mapped here)
+      if (!d_bases[r]) return fail(c, LC_ERR_INVALID, "d_bases[%d] is NULL", r);
+      x.peer[r] = (uint8_t*)d_bases[r];
+    } else {
+      cudaIpcMemHandle_t h;
+      memcpy(&h, (const uint8_t*)ipc_handles + (size_t)r * sizeof h, sizeof h);
+      void* p = nullptr;
+      LC_CUDA(c, cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+      x.peer[r] = (uint8_t*)p;
+      x.ipc[r] = true;
+    }
+  }
+  x.world = world;
+  x.rank = rank;
+  x.connected = true;
+  return LC_OK;
+  LC_GUARD_END(c)
+}
+
+LC_API int32_t lc_exchange_slot(lc_ctx* c, int64_t seq, void** d_slot, int64_t* slot_bytes) {
+  if (!c) return LC_ERR_INVALID;
+  if (!c->xchg.base || seq < 1) return fail(c, LC_ERR_INVALID, "no exchange buffer, or seq < 1");
+  if (d_slot) *d_slot = c->xchg.base + kXchgHeaderBytes + (size_t)(seq & 1) * c->xchg.slot_bytes;
+  if (slot_bytes) *slot_bytes = (int64_t)c->xchg.slot_bytes;
+  return LC_OK;
+}
+
+LC_API int32_t lc_exchange_close(lc_ctx* c) {
+  if (!c) return LC_ERR_INVALID;
+  LC_GUARD_BEGIN
+  LC_TRY(enter_host(c));
+  LC_CUDA(c, cudaStreamSynchronize(c->stream));
+  exchange_release(c);
+  return LC_OK;
+  LC_GUARD_END(c)
+}
+
+LC_API int32_t lc_merge_shards_peer_device(lc_ctx* c, int64_t seq, int32_t n_frames, int64_t slots, int64_t rows, lc_kf_result* d_records_out,
+                                           uint64_t* d_best_out, int32_t phase, void* cuda_stream) {
+  if (!c) return LC_ERR_INVALID;
+  LC_GUARD_BEGIN
+  const auto& x = c->xchg;
+  if (!x.connected) return fail(c, LC_ERR_INVALID, "lc_merge_shards_peer_device before lc_exchange_connect");
+  const int64_t n_rec = (int64_t)n_frames * slots;
+  if (seq < 1 || n_frames < 0 || slots < 0 || rows < 0 || phase < 1 || phase > 3 || (size_t)(n_rec * 16 + rows * 8) > x.slot_bytes)
+    return fail(c, LC_ERR_INVALID, "lc_merge_shards_peer_device: bad shape (%lld records + %lld bests in a slot of %zu B, seq %lld, phase %d)",
+                (long long)n_rec, (long long)rows, x.slot_bytes, (long long)seq, phase);
+  if ((phase & 2) && ((n_rec > 0 && !d_records_out) || (rows > 0 && !d_best_out))) return fail(c, LC_ERR_INVALID, "lc_merge_shards_peer_device: NULL output");
+  if ((uintptr_t)d_records_out % 16 != 0) return fail(c, LC_ERR_INVALID, "lc_merge_shards_peer_device: d_records_out must be 16-byte aligned");
+  LC_CUDA(c, cudaSetDevice(c->cfg.device));
+  StreamScope scope(c, cuda_stream);
+  LC_TRY(scope.enter());
+  PeerBases pb{};
+  for (int r = 0; r < x.world; ++r) pb.base[r] = x.peer[r];
+  const long long items = std::max<long long>(n_rec * x.world, rows);
+  const int grid = (int)std::max<long long>(1, std::min<long long>((items + 255) / 256, c->num_sms));  // one wave: block 0 must be resident
+  merge_peers_kernel<<<grid, 256, 0, scope.st>>>(pb, x.world, x.rank, (unsigned long long)seq, x.slot_bytes, n_rec, rows, (uint4*)d_records_out,
+                                                 d_best_out, phase, 5000000000ull);
   LC_CUDA(c, cudaGetLastError());
   c->launches += 1;
   return LC_OK;

@@ -464,6 +464,66 @@ __global__ void __launch_bounds__(256)
   }
 }
 
+// ---------------------------------------------------------------- the same merge over PEER MEMORY (no collective)
+// Every rank owns an exchange buffer [ header: flags[r] = last sequence number rank r has signalled | slot 0 | slot 1 ] that
+// its peers map (CUDA IPC between processes, plain peer access inside one).  A sharded check writes its [records | bests]
+// contribution into slot (seq & 1) of its OWN buffer; then this one kernel
+//   1. tells every peer "my contribution `seq` is complete" - a release store at system scope into the peer's flag array
+//      (the contribution was written by earlier kernels of the same stream, so it is visible before the flag),
+//   2. waits - acquire loads of its own flags, which the peers write - until every rank has signalled `seq`,
+//   3. reads the peers' slots directly over NVLink (volatile loads: no stale line of an earlier sequence can answer) and
+//      writes the merged records (global keyframe order) and the unsigned minimum of the packed bests locally.
+// No staging buffer, no second kernel.  Slot reuse needs no extra barrier: a rank overwrites slot (seq & 1) at sequence
+// seq + 2, after its kernel of sequence seq + 1 has seen every peer signal seq + 1, which a peer does only after its own
+// kernel of sequence seq - the last reader of that slot - has finished (stream order).
+// The grid is at most one wave, so block 0 (the signaller) is always resident.  A peer that never signals makes the wait
+// give up after `timeout_ns` and trap: an error at the next synchronisation instead of a hung GPU.
+constexpr int kMaxPeers = 16;
+constexpr size_t kXchgHeaderBytes = 1024;
+struct PeerBases {
+  uint8_t* base[kMaxPeers];
+};
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+__global__ void __launch_bounds__(256)
+    merge_peers_kernel(PeerBases peers, int world, int rank, unsigned long long seq, size_t slot_bytes, long long n_rec_per_rank, long long rows,
+                       uint4* __restrict__ rec_out, uint64_t* __restrict__ best_out, int phase, unsigned long long timeout_ns) {
+  if ((phase & 1) && blockIdx.x == 0 && (int)threadIdx.x < world) {
+    __threadfence_system();
+    unsigned long long* flag = reinterpret_cast<unsigned long long*>(peers.base[threadIdx.x]) + rank;
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(flag), "l"(seq) : "memory");
+  }
+  if (!(phase & 2)) return;
+  if ((int)threadIdx.x < world) {
+    const unsigned long long* flag = reinterpret_cast<const unsigned long long*>(peers.base[rank]) + threadIdx.x;
+    const unsigned long long t0 = global_timer_ns();
+    for (;;) {
+      unsigned long long v;
+      asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(flag) : "memory");
+      if (v >= seq) break;
+      if (global_timer_ns() - t0 > timeout_ns) __trap();
+      __nanosleep(100);
+    }
+  }
+  __syncthreads();
+  const size_t slot_off = kXchgHeaderBytes + (size_t)(seq & 1ull) * slot_bytes;
+  const long long tid = blockIdx.x * (long long)blockDim.x + threadIdx.x, stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = tid; i < n_rec_per_rank * world; i += stride) {
+    const int r = (int)(i % world);
+    rec_out[i] = __ldcv(reinterpret_cast<const uint4*>(peers.base[r] + slot_off) + i / world);
+  }
+  const size_t best_off = slot_off + (size_t)n_rec_per_rank * 16;
+  for (long long i = tid; i < rows; i += stride) {
+    uint64_t m = ~0ull;
+    for (int r = 0; r < world; ++r)
+      m = min(m, (uint64_t)__ldcv(reinterpret_cast<const unsigned long long*>(peers.base[r] + best_off) + i));
+    best_out[i] = m;
+  }
+}
+
 __global__ void fill_u64_kernel(uint64_t* p, size_t n, uint64_t v) {
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) p[i] = v;
 }

@@ -10,11 +10,18 @@ bit-exact and order-independent.
 global_row counts rows of all keyframes in insertion order, so the merged best reproduces OpenCV's
 multi-image tie-break (lowest image, then lowest row) whatever the world size.
 
+With CUDA IPC available (one node, NVLink / NVSwitch) the exchange needs no collective at all: every rank writes its
+contribution into a slot of its own exchange buffer, which the peers have mapped, and ONE kernel per rank
+(lc_merge_shards_peer_device) signals the peers, waits for their signals and merges while it reads their slots directly
+over peer memory.  The NCCL all_gather + merge kernel stays as the fallback (and for shard doubles on the CPU).
+
 torch is plumbing here (device buffers, the current CUDA stream, the process group).  The compute is
 liblc_b200's lc_loop_check_batch_device; a `shard` object with the same three methods can be swapped in
 (the CPU tests of the merge logic do that with the oracle over gloo).
 """
 from __future__ import annotations
+
+import os
 
 import numpy as np
 import torch
@@ -79,6 +86,46 @@ class NativeShard:
             rec[:, :nloc] = local
         return rec, best
 
+    # ---- peer-memory exchange (lc_exchange_*): this rank's buffer, mapped by the peers
+    def exchange_setup(self, slot_bytes, group):
+        """Collective.  Returns True when every rank has mapped every peer's exchange buffer."""
+        world, rank = dist.get_world_size(group), dist.get_rank(group)
+        ok, handle = 1, b"\0" * 64
+        try:
+            handle, base = self.ctx.exchange_create(slot_bytes)
+        except _native.LcError:
+            ok = 0
+        handles = [None] * world
+        dist.all_gather_object(handles, (ok, handle), group=group)
+        if all(o for o, _ in handles):
+            try:
+                self.ctx.exchange_connect(world, rank, handles=[h for _, h in handles])
+            except _native.LcError:
+                ok = 0
+        else:
+            ok = 0
+        flag = torch.tensor([ok], dtype=torch.int32, device=self.device)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
+        if int(flag.item()) == 0:
+            try:
+                self.ctx.exchange_close()
+            except _native.LcError:
+                pass
+            return False
+        self._slots = [_wrap_device_memory(self.ctx.exchange_slot(seq)[0], slot_bytes, self.device) for seq in (2, 1)]  # index = seq & 1
+        return True
+
+    def exchange_slot_tensor(self, seq):
+        return self._slots[seq & 1]
+
+    def merge_peers(self, seq, F, slots, world, rows):
+        """One kernel: signal the peers, wait for theirs, merge straight out of their slots."""
+        rec = torch.empty((F, slots * world, 4), dtype=torch.int32, device=self.device)
+        best = torch.empty(rows, dtype=torch.int64, device=self.device)
+        stream = torch.cuda.current_stream(self.device).cuda_stream or 1
+        self.ctx.merge_shards_peer_device(seq, F, slots, rows, rec.data_ptr() if rec.numel() else None, best.data_ptr() if rows else None, 3, stream)
+        return rec, best
+
     def merge(self, gathered: torch.Tensor, contrib_bytes, world, F, slots, rows):
         """gathered: the ranks' contribution buffers back to back (uint8).  One kernel: records in global keyframe order
         [F, slots * world, 4] and the unsigned min of the packed bests [rows]."""
@@ -88,6 +135,17 @@ class NativeShard:
         self.ctx.merge_shards_device(gathered.data_ptr(), contrib_bytes, world, F, slots, rows, rec.data_ptr() if rec.numel() else None,
                                      best.data_ptr() if rows else None, stream)
         return rec, best
+
+
+class _DeviceMemory:
+    """Library-owned device memory as torch sees it (CUDA array interface)."""
+
+    def __init__(self, ptr, nbytes):
+        self.__cuda_array_interface__ = {"shape": (int(nbytes),), "typestr": "|u1", "data": (int(ptr), False), "version": 2}
+
+
+def _wrap_device_memory(ptr, nbytes, device):
+    return torch.as_tensor(_DeviceMemory(ptr, nbytes), device=device)
 
 
 def merge_torch(gathered: torch.Tensor, contrib_bytes, world, F, slots, rows):
@@ -107,7 +165,7 @@ def merge_torch(gathered: torch.Tensor, contrib_bytes, world, F, slots, rows):
 class ShardedLoopDB:
     """Every rank calls every method with the same arguments (SPMD)."""
 
-    def __init__(self, group=None, device=None, shard=None, **cfg):
+    def __init__(self, group=None, device=None, shard=None, exchange=None, **cfg):
         self.group = group
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
@@ -116,9 +174,38 @@ class ShardedLoopDB:
             shard = NativeShard(self.rank, self.world, device, **cfg)
         self.shard = shard
         self.n_keyframes = 0
+        # how the shards' results meet: "p2p" = one kernel over peer memory (CUDA IPC), "nccl" = all_gather + merge kernel,
+        # "auto" = p2p when the group runs on NCCL and every rank can map every peer, else nccl
+        self.exchange = exchange or os.environ.get("LC_SHARD_EXCHANGE", "auto")
+        if self.exchange not in ("auto", "p2p", "nccl"):
+            raise ValueError(f"exchange = {self.exchange!r}: expected auto, p2p or nccl")
+        self._xchg_bytes = 0   # slot size of the live peer exchange (0: none)
+        self._xchg_failed = False
+        self._seq = 0
 
     def owns(self, k):
         return k % self.world == self.rank
+
+    def _peer_exchange(self, contrib_bytes):
+        """Collective decision (every rank sees the same sizes): is the peer-memory exchange usable for this contribution?"""
+        if self.world == 1 or self.exchange == "nccl" or self._xchg_failed or not hasattr(self.shard, "exchange_setup"):
+            return False
+        if self.exchange == "auto" and dist.get_backend(self.group) != "nccl":
+            return False
+        if contrib_bytes <= self._xchg_bytes:
+            return True
+        # (re)create with room to grow; peers may still be reading the old buffers: drain every rank first
+        torch.cuda.synchronize(self.shard.device)
+        dist.barrier(group=self.group)
+        want = max(2 * contrib_bytes, 1 << 22)
+        want = (want + 255) & ~255
+        if self.shard.exchange_setup(want, self.group):
+            self._xchg_bytes, self._seq = want, 0
+            return True
+        if self.exchange == "p2p":
+            raise RuntimeError("exchange='p2p' was asked for but CUDA IPC between the ranks' GPUs is not available")
+        self._xchg_failed, self._xchg_bytes = True, 0
+        return False
 
     def append(self, frame_id, desc, n=None):
         """desc may be None on ranks that do not own this keyframe (then n is required)."""
@@ -185,6 +272,15 @@ class ShardedLoopDB:
         F, rows = len(nq), int(np.sum(nq))
         rec_bytes = F * slots * 16
         contrib_bytes = (rec_bytes + rows * 8 + 15) & ~15
+        if self._peer_exchange(contrib_bytes):
+            # no collective: the contribution goes into this rank's exchange slot, one kernel signals, waits and merges
+            # while it reads the peers' slots over NVLink
+            self._seq += 1
+            contrib = self.shard.exchange_slot_tensor(self._seq)
+            rec = contrib[:rec_bytes].view(torch.int32).view(F, slots, 4)
+            best = contrib[rec_bytes:rec_bytes + rows * 8].view(torch.int64)
+            self.shard.loop_check(d_q, nq, cur, slots, out=(rec, best))
+            return self.shard.merge_peers(self._seq, F, slots, self.world, rows)
         new_buffer = getattr(self.shard, "new_buffer", lambda n: torch.empty(int(n), dtype=torch.uint8))
         contrib = new_buffer(contrib_bytes)
         rec = contrib[:rec_bytes].view(torch.int32).view(F, slots, 4)
