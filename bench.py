@@ -64,7 +64,8 @@ def workload_config(args, world):
     frames = wl.get("frames", 1)
     return {"workload": wl["name"] if not args.keyframes else f"{frames} query frame(s) vs {n_kf}-keyframe DB x {ROWS_PER_KF} rows", "keyframes": n_kf,
             "rows_per_keyframe": ROWS_PER_KF, "nq": NQ, "query_frames": frames, "pairs_per_step": float(frames) * NQ * ROWS_PER_KF * n_kf,
-            "sharding": f"keyframe k -> rank k % {world}; one NCCL all_gather of [records | packed bests] + one merge kernel per step"
+            "sharding": f"keyframe k -> rank k % {world}; one exchange of [records | packed bests] per step: a single kernel over peer "
+                        f"memory (CUDA IPC, NVLink) or, as the fallback, one NCCL all_gather + a merge kernel - see `exchange`"
                         if world > 1 else "single GPU",
             "kernel": args.kernel,
             "timing": f"each arm: {ARM_PAUSE_S:.0f} s idle, warm-up steps, then the timed steps (CUDA events, max over ranks)",
@@ -449,6 +450,8 @@ def main():
                 "api": ("lc_loop_check (C ABI, host buffers)" if F == 1 else "lc_loop_check_batch (C ABI, host buffers)") if world == 1
                        else "ShardedLoopDB.loop_check (host buffers, NCCL merge)"},
         "gpu_launches": int(gpu_launches), "clocks": clocks, "roofline": roof,
+        "exchange": None if world == 1 else ("p2p: lc_merge_shards_peer_device, one kernel signals, waits and merges out of the peers' slots"
+                                             if db._xchg_bytes else "nccl: all_gather_into_tensor + lc_merge_shards_device"),
         "parity": "full-size gate passed: planted-copy record, merged per-query best, sampled keyframes vs CPU oracle",
     }
     if world == 1 and not args.no_extra and F == 1:
