@@ -5,6 +5,7 @@
 // frames_ (reference include/loop_closing.hpp:40,48,69).  No CPU fallback: every compute entry
 // point launches the sm_100a kernels of lc_kernels.cuh or fails with LC_ERR_CUDA.
 #include <cuda_runtime.h>
+#include <nvtx3/nvToolsExt.h>  // header-only; the ranges cost a null-pointer check when no profiler is attached
 
 #include <algorithm>
 #include <cstdarg>
@@ -908,7 +909,13 @@ int check_rows(lc_ctx* c, const char* what, const uint8_t* p, int32_t n, size_t 
 
 // =================================================================== extern "C"
 #define LC_API extern "C" __attribute__((visibility("default")))
-#define LC_GUARD_BEGIN try {
+// every entry point that touches the GPU runs inside an NVTX range named after it (ncu --nvtx --nvtx-include "lc_loop_check/",
+// Nsight Systems timelines): the tracing hook of SURVEY.md section 5
+struct NvtxRange {
+  explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+  ~NvtxRange() { nvtxRangePop(); }
+};
+#define LC_GUARD_BEGIN NvtxRange nvtx_range_(__func__); try {
 #define LC_GUARD_END(c)                                          \
   }                                                              \
   catch (const std::bad_alloc&) { return fail((c), LC_ERR_NOMEM, "host allocation failed"); } \
