@@ -197,7 +197,7 @@ class ShardedLoopDB:
         # (re)create with room to grow; peers may still be reading the old buffers: drain every rank first
         torch.cuda.synchronize(self.shard.device)
         dist.barrier(group=self.group)
-        want = max(2 * contrib_bytes, 1 << 22)
+        want = max(2 * contrib_bytes, int(os.environ.get("LC_SHARD_SLOT_MIN", 1 << 22)))  # (the knob lets tests force regrowth)
         want = (want + 255) & ~255
         if self.shard.exchange_setup(want, self.group):
             self._xchg_bytes, self._seq = want, 0
