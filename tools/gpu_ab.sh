@@ -1,5 +1,9 @@
 #!/bin/bash
-# A/B of two builds of the library on the C4-sized check (sustained load: the power cap decides): alternate them
+# A/B of two builds of the library on the C4-sized check (sustained load: the power cap decides): alternate them.
+# The alternative build of profiles/r02_ab_zero_one_train.txt (both operands +1/-1, the round-1 encoding) is made here, on the CPU box, with
+#   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC,-fvisibility=hidden -shared \
+#        -DLC_FX_ZERO_ONE_TRAIN=0 -o build/liblc_b200_pm1.so slam_loop_closing_b200/csrc/lc_abi.cu
+# and selected at run time with LC_B200_LIB (slam_loop_closing_b200/_native.py).
 set -u
 mkdir -p gpurun_out
 OUT=gpurun_out/${1:-ab}.txt
