@@ -326,6 +326,13 @@ int32_t lc_l2_loop_check(lc_ctx* ctx, const void* q, int32_t nq, size_t q_stride
                          int32_t current_frame_id, int32_t loop_gap, double ratio, int32_t min_rows,
                          lc_l2_result* results, int64_t results_cap, int64_t* n_results);
 
+/* The whole matching step of the shipped loop search (src/main.cpp:1375-1389: for curr, for past <= curr - loopGap:
+ * matchFeatures(desc[curr], desc[past], 0.7)) in one call, the query side being the RESIDENT store itself: stored views
+ * first_view .. first_view + n_query_views - 1, each against every stored view; results is [n_query_views][n_views]
+ * (*n_views = number of stored views), n_good = -1 where main.cpp skips the pair.  Nothing is uploaded.  Unsharded contexts. */
+int32_t lc_l2_loop_search(lc_ctx* ctx, int64_t first_view, int32_t n_query_views, int32_t loop_gap, double ratio,
+                          int32_t min_rows, lc_l2_result* results, int64_t results_cap, int64_t* n_views);
+
 /* ---- measurement aid: the peak of the pipe the default loop-check kernel runs on.  For about `milliseconds` every SM
  *      issues nothing but tcgen05.mma kind::mxf4 (M 128 x N 256 x K 64, operands in shared memory, the match kernel's
  *      value distribution); *mac_per_s = multiply-accumulates per second of the whole GPU (a descriptor pair is 256 of

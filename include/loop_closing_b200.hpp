@@ -210,6 +210,17 @@ class SiftMatcher {
     out.resize(static_cast<size_t>(n));
     return out;
   }
+  // the whole double loop of main.cpp:1375-1389 in one call: counts[curr - loopGap][past] for curr = loopGap .. numViews - 1
+  std::vector<std::vector<lc_l2_result>> loopSearch(int loopGap, double ratio = 0.7, int min_rows = 100) {
+    int64_t n_views = 0;
+    ok(lc_l2_db_size(ctx_, &n_views, nullptr));
+    const int n_query = n_views > loopGap ? static_cast<int>(n_views - loopGap) : 0;
+    std::vector<lc_l2_result> flat(static_cast<size_t>(n_query) * static_cast<size_t>(n_views));
+    ok(lc_l2_loop_search(ctx_, loopGap, n_query, loopGap, ratio, min_rows, flat.data(), static_cast<int64_t>(flat.size()), nullptr));
+    std::vector<std::vector<lc_l2_result>> out(static_cast<size_t>(n_query));
+    for (int f = 0; f < n_query; ++f) out[f].assign(flat.begin() + static_cast<size_t>(f) * n_views, flat.begin() + static_cast<size_t>(f + 1) * n_views);
+    return out;
+  }
 
  private:
   static int32_t type_of(const cv::Mat& d) {

@@ -71,6 +71,7 @@ SYMBOLS = {
     "lc_l2_db_clear": (_i32, [_vp]),
     "lc_l2_match_pair": (_i32, [_vp, _vp, _i32, _sz, _vp, _i32, _sz, _i32, C.c_double, _vp, _vp, _vp, _vp, _pi32]),
     "lc_l2_loop_check": (_i32, [_vp, _vp, _i32, _sz, _i32, _i32, _i32, C.c_double, _i32, _vp, _i64, _vp]),
+    "lc_l2_loop_search": (_i32, [_vp, _i64, _i32, _i32, C.c_double, _i32, _vp, _i64, _vp]),
     "lc_loop_check_begin": (_i32, [_vp, _vp, _i32, _sz, _i32, _i32]),
     "lc_loop_check_end": (_i32, [_vp, _vp, _i64, _vp, _vp]),
     "lc_loop_check": (_i32, [_vp, _vp, _i32, _sz, _i32, _vp, _i64, _pi64, _vp]),
@@ -350,6 +351,16 @@ class Context:
         self._ck(self._lib.lc_l2_loop_check(self._h, _ptr(qa), len(qa), qs, ty, int(current_frame_id), int(loop_gap),
                                             float(ratio), int(min_rows), _ptr(res), nloc, C.byref(n)))
         return res[:n.value]
+
+    def l2_loop_search(self, first_view, n_query_views, loop_gap, ratio=0.7, min_rows=100):
+        """The shipped loop search's matching step for stored views first_view .. first_view + n_query_views - 1 against the
+        whole resident store: L2_RESULT array [n_query_views, n_views]."""
+        n_views = self.l2_db_size()["keyframes"]
+        res = np.zeros((int(n_query_views), n_views), L2_RESULT)
+        n = C.c_int64()
+        self._ck(self._lib.lc_l2_loop_search(self._h, int(first_view), int(n_query_views), int(loop_gap), float(ratio), int(min_rows), _ptr(res),
+                                             res.size, C.byref(n)))
+        return res
 
     # ---- detectLoops
     def loop_check(self, q, current_frame_id, want_best=True):

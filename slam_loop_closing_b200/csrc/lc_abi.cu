@@ -2154,6 +2154,57 @@ LC_API int32_t lc_l2_loop_check(lc_ctx* c, const void* q, int32_t nq, size_t qs,
   LC_GUARD_END(c)
 }
 
+// The shipped loop search's matching step as a whole (src/main.cpp:1375-1389): every stored view `curr` of a range against
+// every stored view at least loop_gap before it.  The query side is the resident store itself - nothing is uploaded.
+LC_API int32_t lc_l2_loop_search(lc_ctx* c, int64_t first_view, int32_t n_query_views, int32_t loop_gap, double ratio, int32_t min_rows,
+                                 lc_l2_result* results, int64_t cap, int64_t* n_views) {
+  if (!c) return LC_ERR_INVALID;
+  LC_GUARD_BEGIN
+  auto& S = c->l2s;
+  if (c->cfg.shard_world != 1) return fail(c, LC_ERR_INVALID, "lc_l2_loop_search needs an unsharded context (the query views must be resident here)");
+  const int64_t n_kf = (int64_t)S.h_kf.size();
+  if (n_views) *n_views = n_kf;
+  if (first_view < 0 || n_query_views < 0 || first_view + n_query_views > n_kf)
+    return fail(c, LC_ERR_INVALID, "query views [%lld, %lld) outside the %lld stored views", (long long)first_view, (long long)(first_view + n_query_views), (long long)n_kf);
+  const int64_t need = (int64_t)n_query_views * n_kf;
+  if (need > 0 && (!results || cap < need)) return fail(c, LC_ERR_CAPACITY, "results_cap %lld < %lld", (long long)cap, (long long)need);
+  if (need == 0) return LC_OK;
+  if (c->pending.active) return fail(c, LC_ERR_INVALID, "a loop check or a frame is pending (its timing events are in use)");
+  LC_TRY(enter_host(c));
+  timing_begin(c);
+  if (S.synced != S.h_kf.size()) {
+    LC_TRY(ensure(c, S.d_kf, S.h_kf.size() * sizeof(l2::L2Kf)));
+    LC_CUDA(c, cudaMemcpyAsync(S.d_kf.p, S.h_kf.data(), S.h_kf.size() * sizeof(l2::L2Kf), cudaMemcpyHostToDevice, c->stream));
+    LC_CUDA(c, cudaStreamSynchronize(c->stream));
+    S.synced = S.h_kf.size();
+  }
+  if (c->timing_on) LC_CUDA(c, cudaEventRecord(c->ev[1], c->stream));
+  constexpr int kChunk = 64;  // query views per launch: bounds the packed query images (4 x 128 KiB per 4000-row view)
+  LC_TRY(ensure(c, c->d_l2frames, (size_t)kChunk * sizeof(l2::L2Frame)));
+  LC_TRY(ensure(c, c->d_l2res, (size_t)kChunk * n_kf * sizeof(l2::L2Result)));
+  LC_TRY(ensure_pin_down(c, (size_t)kChunk * n_kf * sizeof(l2::L2Result)));
+  static_assert(sizeof(lc_l2_result) == sizeof(l2::L2Result), "record layouts differ");
+  for (int32_t f0 = 0; f0 < n_query_views; f0 += kChunk) {
+    const int nf = std::min<int>(kChunk, n_query_views - f0);
+    std::vector<l2::L2Frame> hf((size_t)nf);
+    for (int f = 0; f < nf; ++f) {
+      const l2::L2Kf& v = S.h_kf[(size_t)(first_view + f0 + f)];
+      hf[f] = l2::L2Frame{v.rows, v.norms, v.n, v.frame_id, nullptr, nullptr, nullptr, nullptr};
+    }
+    LC_CUDA(c, cudaMemcpyAsync(c->d_l2frames.p, hf.data(), hf.size() * sizeof(l2::L2Frame), cudaMemcpyHostToDevice, c->stream));  // pageable: staged before it returns
+    LC_TRY(l2_run(c, (const l2::L2Kf*)S.d_kf.p, (int)n_kf, (const l2::L2Frame*)c->d_l2frames.p, hf.data(), nf, (l2::L2Result*)c->d_l2res.p,
+                  l2::L2Knobs{loop_gap, min_rows, ratio}));
+    const size_t bytes = (size_t)nf * n_kf * sizeof(l2::L2Result);
+    LC_CUDA(c, cudaMemcpyAsync(c->pin_down, c->d_l2res.p, bytes, cudaMemcpyDeviceToHost, c->stream));
+    LC_CUDA(c, cudaStreamSynchronize(c->stream));
+    memcpy(results + (size_t)f0 * n_kf, c->pin_down, bytes);
+  }
+  if (c->timing_on) LC_CUDA(c, cudaEventRecord(c->ev[2], c->stream));
+  LC_TRY(timing_end(c, false));
+  return LC_OK;
+  LC_GUARD_END(c)
+}
+
 // ------------------------------------------------------------------- the FP4 pipe's measured peak
 LC_API int32_t lc_probe_mxf4_peak(lc_ctx* c, int32_t milliseconds, double* mac_per_s, double* sm_mhz) {
   if (!c) return LC_ERR_INVALID;

@@ -18,7 +18,8 @@ int main() {
     s.matchFeatures(d, d, good, 0.75);
     s.addView(0, d);
     auto r = s.loopMatchCounts(d, 5, 3);
-    return static_cast<int>(fm.size() + fl.size() + g.size() + l.size() + l2.size() + c.size() + good.size() + r.size());
+    auto ls = s.loopSearch(3);
+    return static_cast<int>(fm.size() + fl.size() + g.size() + l.size() + l2.size() + c.size() + good.size() + r.size() + ls.size());
   } catch (const std::exception&) {
     return 0;  // no B200 here: lc_create throws, which is the point of "no CPU fallback"
   }

@@ -183,3 +183,38 @@ def test_l2_rejects_non_sift_values(lc):
             c.l2_db_append(0, np.full((3, 128), 0.5, np.float32))
         with pytest.raises(lc.LcError):
             c.l2_match_pair(np.full((3, 128), 300.0, np.float32), np.zeros((3, 128), np.float32))
+
+
+def test_l2_loop_search_over_the_resident_store(lc):
+    """lc_l2_loop_search: the shipped loop search's double loop (src/main.cpp:1375-1389: every curr >= loopGap against every
+    past <= curr - loopGap) in one call, the queries being the stored views themselves - against the oracle pair by pair and
+    against the per-view call; more query views than one launch takes (chunks of 64), ragged views, one below min_rows, one empty."""
+    rng = np.random.default_rng(11)
+    V, gap = 75, 6
+    views = []
+    for k in range(V):
+        n = 0 if k == 40 else 60 if k == 13 else int(rng.integers(150, 420))
+        v = rng.integers(0, 200, (n, 128)).astype(np.uint8)
+        if k >= 30 and k % 4 == 0 and len(views[k - 30]) and n:  # the walk returns: view k overlaps view k - 30
+            m = min(n, len(views[k - 30]), 250)
+            v[:m] = np.clip(views[k - 30][:m].astype(np.int32) + rng.integers(-2, 3, (m, 128)), 0, 255).astype(np.uint8)
+        views.append(v)
+    with lc.Context() as c:
+        for k, v in enumerate(views):
+            c.l2_db_append(k, v)
+        res = c.l2_loop_search(gap, V - gap, gap, 0.7, 100)
+        assert res.shape == (V - gap, V)
+        for f, curr in enumerate(range(gap, V)):
+            want = l2_oracle.loop_check(views[curr], views, list(range(V)), curr, gap, 0.7, 100, nthreads=16)
+            np.testing.assert_array_equal(res[f], want, err_msg=f"curr {curr}")
+            if curr % 17 == 0:
+                np.testing.assert_array_equal(res[f], c.l2_loop_check(views[curr], curr, gap, 0.7, 100))
+        assert (res["n_good"] > 60).sum() >= 5  # the revisits stand out
+        assert (res[40 - gap]["n_good"] == -1).all() and (res[13 - gap]["n_good"] == -1).all()  # empty / too small query views
+        with pytest.raises(lc.LcError):
+            c.l2_loop_search(70, 10, gap)  # past the end of the store
+        assert c.l2_loop_search(0, 0, gap).shape == (0, V)
+    with lc.Context(shard_rank=0, shard_world=2) as c:
+        c.l2_db_append(0, views[0])
+        with pytest.raises(lc.LcError):
+            c.l2_loop_search(0, 1, 0)
