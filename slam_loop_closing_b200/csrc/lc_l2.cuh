@@ -18,7 +18,12 @@
 // 2.5 alu instructions per pair (against 0.5 for the Hamming maximum) and bound the first version of this kernel at
 // about 640 cycles per tile against the MMA's 256; the epilogue is therefore a tournament: the minimum of every aligned
 // group of 8 columns, the two smallest of the group minima (0.8 alu instructions per pair), and the 7 other rows of the
-// single best group rescanned once per (query, view) at the end.
+// single best group rescanned once per (query, view) at the end.  Even so a tile costs an epilogue thread about 140 dependent
+// instructions behind a TMEM load; two warps per scheduler could not hide that (round 1: issue slots 58 % busy), so the
+// epilogue is TWO sets of eight warps that drain alternate query tiles (four warps per scheduler, issue slots 73 %).  640
+// threads would leave 96 registers per thread - too few for both 32-column loads of a half tile in flight - so the warp
+// group of the loaders, the MMA issuer and the spare warp hands registers over with setmaxnreg (64 there, 104 in the
+// epilogue; the loaders fetch a tile in two rounds of eight 16-byte loads per thread instead of one round of sixteen).
 #pragma once
 #include "lc_mxf4.cuh"
 
@@ -51,10 +56,14 @@ constexpr int kOffXch = kOffKc + kBStages * kTN * 4;        // [tile][row] x {d1
 constexpr int kXchBytes = kQTilesPerCta * kQTile * 3 * 4;
 constexpr int kOffBar = kOffXch + kXchBytes;
 constexpr int kSmemAlloc = kOffBar + 256;    // 194,304 B
-constexpr int kEpiWarps = 8;                 // warp w: TMEM lane quadrant w % 4, column half w / 4
+constexpr int kEpiSets = 2;                  // two sets of epilogue warps drain alternate query tiles (set = tile m & 1)
+constexpr int kSetWarps = 8;                 // per set: warp w -> TMEM lane quadrant w % 4, column half w / 4
+constexpr int kEpiWarps = kEpiSets * kSetWarps;
 constexpr int kLoadWarps = 2;
 constexpr int kMmaWarp = kEpiWarps + kLoadWarps;
-constexpr int kThreads = 384;                // 12 warps (the last one idle): 168 registers per thread
+constexpr int kThreads = 640;                // 20 warps (the last one idle), launched with 96 registers per thread
+constexpr int kEpiRegs = 104;                // setmaxnreg: the epilogue warps take what the loader / MMA warp group gives up
+constexpr int kOtherRegs = 64;
 constexpr int kNone = 0x7f000000;            // scan constant of a pad column: never among the two smallest of real rows
 constexpr int kNoD2 = 0x7fffffff;            // "no such neighbour"
 
@@ -237,7 +246,7 @@ __global__ void __launch_bounds__(kThreads, 1)
     }
     for (int i = 0; i < kAccStages; ++i) {
       mbar_init(bars + 1 + 2 * kBStages + i, 1);
-      mbar_init(bars + 1 + 2 * kBStages + kAccStages + i, kEpiWarps);
+      mbar_init(bars + 1 + 2 * kBStages + kAccStages + i, kSetWarps);  // the one set that drains this use of the stage
     }
     mbar_fence_init();
   }
@@ -246,6 +255,9 @@ __global__ void __launch_bounds__(kThreads, 1)
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // warp groups 0-3 are the epilogue, warp group 4 holds the loaders, the MMA issuer and a spare warp
+  if (warp >= kEpiWarps) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kOtherRegs));
+  else asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kEpiRegs));
 
   if (warp == kMmaWarp) {
     // ===================== MMA issuer =====================
@@ -308,9 +320,11 @@ __global__ void __launch_bounds__(kThreads, 1)
       if (!view_eligible(fr, kf, kb)) continue;
       for (int row0 = 0; row0 < kf.n; row0 += kTN) {
         const int cnt = min(kTN, kf.n - row0);
-        uint4 v[16];
+        // 1024 16-byte chunks per tile, 64 threads: two rounds of eight loads in flight per thread (the registers of this
+        // warp group have gone to the epilogue)
+        uint4 v[8];
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {  // 1024 16-byte chunks per tile, 64 threads
+        for (int i = 0; i < 8; ++i) {
           const int u = et + i * 64, r = u >> 3;
           v[i] = r < cnt ? __ldg(kf.rows + (size_t)(row0 + r) * 8 + (u & 7)) : make_uint4(0, 0, 0, 0);
         }
@@ -324,8 +338,18 @@ __global__ void __launch_bounds__(kThreads, 1)
         par_bempty ^= 1u << bb;
         uint8_t* tile = sB + bb * kBTileBytes;
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
+        for (int i = 0; i < 8; ++i) {
           const int u = et + i * 64;
+          *reinterpret_cast<uint4*>(tile + fx::tile_offset(u >> 3, u & 7)) = v[i];
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int u = et + (i + 8) * 64, r = u >> 3;
+          v[i] = r < cnt ? __ldg(kf.rows + (size_t)(row0 + r) * 8 + (u & 7)) : make_uint4(0, 0, 0, 0);
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int u = et + (i + 8) * 64;
           *reinterpret_cast<uint4*>(tile + fx::tile_offset(u >> 3, u & 7)) = v[i];
         }
         sKc[bb * kTN + et] = kc[0];
@@ -337,25 +361,27 @@ __global__ void __launch_bounds__(kThreads, 1)
       }
     }
   } else {
-    // ===================== epilogue (256 threads: warp w owns TMEM lanes 32 (w % 4).., column half w / 4) =====================
-    const int quad = warp & 3, half = warp >> 2;
+    // ===================== epilogue (512 threads = 2 sets x 8 warps; in a set warp w owns TMEM lanes 32 (w % 4).., column half w / 4) ==========
+    // Set s drains the query tiles m with m % 2 == s; both sets walk the same tile sequence and count every tile, so each knows
+    // the accumulator stage and barrier phase of its own tiles without looking at the other's.
+    const int set = warp >> 3, w8 = warp & 7, quad = w8 & 3, half = w8 >> 2;
     const int row = quad * 32 + lane;
     const uint32_t tmem_rows = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(half * 64);
-    uint32_t st = 0, acc_par = 0, par_bfull = 0;
+    uint32_t t = 0, par_bfull = 0;
     int bb = 0;
-    // |q|^2 of the queries this thread finishes (tiles m with m % 2 == half)
-    int na[kQTilesPerCta / 2];
+    // |q|^2 of the queries this thread finishes: tiles m = set + 2 i with i % 2 == half
+    int na[2];
 #pragma unroll
-    for (int j = 0; j < kQTilesPerCta / 2; ++j) {
-      const int q = ab.q0 + (2 * j + half) * kQTile + row;
-      na[j] = q < fr.nq ? (int)__ldg(fr.norms + q) : 0;
+    for (int jj = 0; jj < 2; ++jj) {
+      const int q = ab.q0 + (set + 2 * (2 * jj + half)) * kQTile + row;
+      na[jj] = q < fr.nq ? (int)__ldg(fr.norms + q) : 0;
     }
     for (int k = slot; k < n_kf; k += n_slots) {
       const L2Kf kf = kfs[k];
       if (!view_eligible(fr, kf, kb)) continue;
-      Knn2 best[kQTilesPerCta];
+      Knn2 best[kQTilesPerCta / 2];  // best[i]: tile m = set + 2 i
 #pragma unroll
-      for (int m = 0; m < kQTilesPerCta; ++m) best[m].reset();
+      for (int i = 0; i < kQTilesPerCta / 2; ++i) best[i].reset();
       for (int row0 = 0; row0 < kf.n; row0 += kTN) {
         // the tile's scan constants (visible once the loaders' b_full arrival has been observed)
         mbar_wait_a(b_full + 8 * bb, (par_bfull >> bb) & 1);
@@ -364,38 +390,41 @@ __global__ void __launch_bounds__(kThreads, 1)
 #pragma unroll
         for (int m = 0; m < kQTilesPerCta; ++m) {
           if (m < m_tiles) {
-            mbar_wait_a(acc_full + 8 * st, acc_par);
-            tc_fence_after();
-            int a[32], b[32];
-            tmem_ld32(tmem_rows + st * kTN, a);
-            tmem_ld32(tmem_rows + st * kTN + 32, b);
-            tmem_ld_wait();
-            fx::release_stage(acc_empty + 8 * st);
-            // Tournament: the minimum of every aligned group of 8 columns (4 min3/min per 8 keys), then the two smallest
-            // of the 8 group minima.  m1 is the half-tile's smallest key; m2 is the smallest key OUTSIDE m1's group - the
-            // other 7 keys of that one group are looked at once per (query, view) at the very end (rescan_group), not here.
-            Top2 t2;
-            t2.reset();
+            if ((m & 1) == set) {
+              const uint32_t st = t & (kAccStages - 1), acc_par = (t / kAccStages) & 1u;
+              mbar_wait_a(acc_full + 8 * st, acc_par);
+              tc_fence_after();
+              int a[32], b[32];
+              tmem_ld32(tmem_rows + st * kTN, a);
+              tmem_ld32(tmem_rows + st * kTN + 32, b);
+              tmem_ld_wait();
+              fx::release_stage(acc_empty + 8 * st);
+              // Tournament: the minimum of every aligned group of 8 columns (4 min3/min per 8 keys), then the two smallest
+              // of the 8 group minima.  m1 is the half-tile's smallest key; m2 is the smallest key OUTSIDE m1's group - the
+              // other 7 keys of that one group are looked at once per (query, view) at the very end (rescan_group), not here.
+              Top2 t2;
+              t2.reset();
 #pragma unroll
-            for (int j = 0; j < 32; j += 16) {  // key = -256 * dot + (|t|^2 * 128 + column)
-              int g[4];
+              for (int j = 0; j < 32; j += 16) {  // key = -256 * dot + (|t|^2 * 128 + column)
+                int g[4];
 #pragma unroll
-              for (int u = 0; u < 2; ++u) {
-                const int4 k0 = kc4[(j >> 2) + 2 * u], k1 = kc4[(j >> 2) + 2 * u + 1];
-                const int4 k2 = kc4[8 + (j >> 2) + 2 * u], k3 = kc4[8 + (j >> 2) + 2 * u + 1];
-                const int c = j + 8 * u;
-                g[u] = group_min8(a[c] * -256 + k0.x, a[c + 1] * -256 + k0.y, a[c + 2] * -256 + k0.z, a[c + 3] * -256 + k0.w,
-                                  a[c + 4] * -256 + k1.x, a[c + 5] * -256 + k1.y, a[c + 6] * -256 + k1.z, a[c + 7] * -256 + k1.w);
-                g[2 + u] = group_min8(b[c] * -256 + k2.x, b[c + 1] * -256 + k2.y, b[c + 2] * -256 + k2.z, b[c + 3] * -256 + k2.w,
-                                      b[c + 4] * -256 + k3.x, b[c + 5] * -256 + k3.y, b[c + 6] * -256 + k3.z, b[c + 7] * -256 + k3.w);
+                for (int u = 0; u < 2; ++u) {
+                  const int4 k0 = kc4[(j >> 2) + 2 * u], k1 = kc4[(j >> 2) + 2 * u + 1];
+                  const int4 k2 = kc4[8 + (j >> 2) + 2 * u], k3 = kc4[8 + (j >> 2) + 2 * u + 1];
+                  const int c = j + 8 * u;
+                  g[u] = group_min8(a[c] * -256 + k0.x, a[c + 1] * -256 + k0.y, a[c + 2] * -256 + k0.z, a[c + 3] * -256 + k0.w,
+                                    a[c + 4] * -256 + k1.x, a[c + 5] * -256 + k1.y, a[c + 6] * -256 + k1.z, a[c + 7] * -256 + k1.w);
+                  g[2 + u] = group_min8(b[c] * -256 + k2.x, b[c + 1] * -256 + k2.y, b[c + 2] * -256 + k2.z, b[c + 3] * -256 + k2.w,
+                                        b[c + 4] * -256 + k3.x, b[c + 5] * -256 + k3.y, b[c + 6] * -256 + k3.z, b[c + 7] * -256 + k3.w);
+                }
+                t2.push2(g[0], g[1]);
+                t2.push2(g[2], g[3]);
               }
-              t2.push2(g[0], g[1]);
-              t2.push2(g[2], g[3]);
+              // tile-local (distance part, column) -> running neighbours; rows of later tiles are higher
+              const int e1 = t2.m1 >> 7, j1 = row0 + (t2.m1 & 127), e2 = t2.m2 >> 7;
+              best[m >> 1].merge_later(e1, j1, e2);
             }
-            // tile-local (distance part, column) -> running neighbours; rows of later tiles are higher
-            const int e1 = t2.m1 >> 7, j1 = row0 + (t2.m1 & 127), e2 = t2.m2 >> 7;
-            best[m].merge_later(e1, j1, e2);
-            if (++st == kAccStages) st = 0, acc_par ^= 1;
+            ++t;
           }
         }
         __syncwarp();
@@ -405,31 +434,34 @@ __global__ void __launch_bounds__(kThreads, 1)
       // the two column halves of a row meet in shared memory: half h hands over the tiles it does not finish
       // (pad columns carry kNone >> 7 = 0xfe0000 + ... as distance part: far above any real one, see below)
 #pragma unroll
-      for (int m = 0; m < kQTilesPerCta; ++m)
-        if ((m & 1) != half && m < m_tiles) {
+      for (int i = 0; i < kQTilesPerCta / 2; ++i) {
+        const int m = set + 2 * i;
+        if ((i & 1) != half && m < m_tiles) {
           int* x = xch + (m * kQTile + row) * 3;
-          x[0] = best[m].d1, x[1] = best[m].i1, x[2] = best[m].d2;
+          x[0] = best[i].d1, x[1] = best[i].i1, x[2] = best[i].d2;
         }
-      asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory");
+      }
+      if (set == 0) asm volatile("bar.sync 1, %0;" ::"n"(kSetWarps * 32) : "memory");  // one named barrier per set
+      else asm volatile("bar.sync 2, %0;" ::"n"(kSetWarps * 32) : "memory");
       int cnt_good = 0;
 #pragma unroll
-      for (int j = 0; j < kQTilesPerCta / 2; ++j) {
-        const int m = 2 * j + half, ql = m * kQTile + row;
+      for (int jj = 0; jj < 2; ++jj) {
+        const int m = set + 2 * (2 * jj + half), ql = m * kQTile + row;
         if (m < m_tiles && ql < nq_blk) {
-          Knn2 r = half ? best[2 * j + 1] : best[2 * j];
+          Knn2 r = half ? best[2 * jj + 1] : best[2 * jj];
           const int* x = xch + (m * kQTile + row) * 3;
           r.merge_any(x[0], x[1], x[2]);
           // distance parts -> squared distances; a pad column's part (>= kNone >> 7) means "no such row"
           const int limit = kNone >> 7;
-          const int d1 = r.d1 >= limit ? kNoD2 : r.d1 + na[j];
-          int d2 = r.d2 >= limit ? kNoD2 : r.d2 + na[j];
+          const int d1 = r.d1 >= limit ? kNoD2 : r.d1 + na[jj];
+          int d2 = r.d2 >= limit ? kNoD2 : r.d2 + na[jj];
           // so far d2 is the nearest row OUTSIDE the best row's group of 8; the 7 rows inside it are the last candidates.
           // They can only lower d2, so a ratio test that already fails stays failed: the rescan is needed only for the
           // queries that pass so far (few, except against a view of the same place) and when the caller wants d2 itself.
           bool g = ratio_test(d1, d2, kb.ratio);
           if (d1 != kNoD2 && (g || d2 == kNoD2 || fr.d2 != nullptr)) {  // (no row outside the group at all: it decides alone)
             const int e = rescan_group(fr.q + (size_t)(ab.q0 + ql) * 8, kf, r.i1);
-            if (e != kNoD2) d2 = min(d2, e + na[j]);
+            if (e != kNoD2) d2 = min(d2, e + na[jj]);
             g = ratio_test(d1, d2, kb.ratio);
           }
           cnt_good += g ? 1 : 0;
@@ -442,7 +474,9 @@ __global__ void __launch_bounds__(kThreads, 1)
       }
       cnt_good = __reduce_add_sync(0xffffffffu, cnt_good);
       if (lane == 0 && cnt_good) atomicAdd(&results[(size_t)ab.frame * n_kf + k].n_good, cnt_good);
-      asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory");  // the exchange buffer is free again
+      // this set's part of the exchange buffer is free again
+      if (set == 0) asm volatile("bar.sync 1, %0;" ::"n"(kSetWarps * 32) : "memory");
+      else asm volatile("bar.sync 2, %0;" ::"n"(kSetWarps * 32) : "memory");
     }
   }
   tc_fence_before();
