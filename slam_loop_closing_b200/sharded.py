@@ -192,6 +192,8 @@ class ShardedLoopDB:
             return False
         if self.exchange == "auto" and dist.get_backend(self.group) != "nccl":
             return False
+        if contrib_bytes == 0:
+            return False  # nothing to exchange (no query frames): the fallback path handles the empty case
         if contrib_bytes <= self._xchg_bytes:
             return True
         # (re)create with room to grow; peers may still be reading the old buffers: drain every rank first
