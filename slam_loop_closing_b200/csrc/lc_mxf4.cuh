@@ -89,6 +89,10 @@ using tc::CtaWork;
 //                per-QUERY constant added once per (keyframe, query) result, and half of all products are exact zeros -
 //                the multipliers and adders they would toggle are what a power-capped B200 spends its clock on.
 //   0            both sides +1.0 / -1.0:  D = 256 - 2 hamming.
+// LC_FX_DRAIN_EXPERIMENT: timing experiments of tools/gpu_r02c.sh (wrong results), 0 in every shipped build
+#ifndef LC_FX_DRAIN_EXPERIMENT
+#define LC_FX_DRAIN_EXPERIMENT 0
+#endif
 #ifndef LC_FX_ZERO_ONE_TRAIN
 #define LC_FX_ZERO_ONE_TRAIN 1
 #endif
@@ -243,10 +247,22 @@ __device__ __forceinline__ float drain_accumulator(uint32_t taddr, int ncols, ui
     tmem_ld16(taddr + 96, d);
     tmem_ld_wait();
     release_stage(acc_empty);
+#if LC_FX_DRAIN_EXPERIMENT == 1    // WRONG RESULTS, timing only: all TMEM loads, (almost) no fold
+    mx.m0 = fmaxf(__int_as_float(a[0]), __int_as_float(b[0]));
+    mx.m1 = fmaxf(__int_as_float(c[0]), __int_as_float(d[0]));
+#elif LC_FX_DRAIN_EXPERIMENT == 2  // WRONG RESULTS, timing only: 64 of the 112 columns loaded and folded
+    mx.fold(a);
+    mx.fold(b);
+#elif LC_FX_DRAIN_EXPERIMENT == 3  // WRONG RESULTS, timing only: all loads, 64 of the 112 columns folded
+    mx.fold(a);
+    mx.fold(b);
+    mx.m1 = fmaxf(mx.m1, fmaxf(__int_as_float(c[0]), __int_as_float(d[0])));
+#else
     mx.fold(a);
     mx.fold(b);
     mx.fold(c);
     mx.fold(d);
+#endif
   } else {  // the last tile of a keyframe: 16 columns at a time
 #pragma unroll 1
     for (int col = 0; col < ncols; col += 16) {

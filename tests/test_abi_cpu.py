@@ -130,3 +130,20 @@ def test_select_candidates_runs_on_host():
     assert got == [(2, 0, 60, 0.6), (3, 0, 60, 0.6), (3, 1, 61, 61 / 101), (4, 0, 60, 0.6), (4, 1, 61, 61 / 101),
                    (4, 2, 62, 62 / 102)]
     assert s.consecutive_matches_ == [100, 101, 102, 103]
+
+
+def test_tmem_loads_are_waited_for():
+    """Static check of the built sm_100a code (tools/sass_ldtm_check.py): every TMEM load has been waited for before the
+    next mbarrier arrival.  `tcgen05.wait::ld` becomes scoreboard waits only for loads in its own basic block; a kernel
+    change that separates them hands an accumulator stage back while it is still being read (profiles/r02_ab_drain_schedule.txt)."""
+    import shutil
+    import subprocess
+    import sys
+    import slam_loop_closing_b200 as m
+    if shutil.which("cuobjdump") is None:
+        pytest.skip("cuobjdump not on PATH")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "sass_ldtm_check.py"), m.library_path()],
+                       capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    n_ldtm = int(re.search(r"(\d+) LDTM", r.stdout).group(1))
+    assert n_ldtm >= 50, r.stdout  # the three tensor kernels were really looked at
