@@ -1,6 +1,6 @@
 #!/bin/bash
-# round 2, session 2: what does the drain cost the tensor pipe?  Timing-only builds (wrong results, -DLC_FX_DRAIN_EXPERIMENT=1/2/3):
-# x1 = all TMEM loads, no fold; x2 = 64 of 112 columns loaded and folded; x3 = all loads, 64 columns folded
+# round 2, session 2: seven 16-column TMEM loads per drain instead of 32 + 32 + 32 + 16 (-DLC_FX_DRAIN_X16=1)
 set -u
 mkdir -p gpurun_out
-bash tools/gpu_abn.sh ab_drain_cost 50000 2 build/liblc_b200_old.so build/liblc_b200_x1.so build/liblc_b200_x2.so build/liblc_b200_x3.so
+bash tools/gpu_abn.sh ab_x16 50000 3 build/liblc_b200_x16.so
+LC_B200_LIB=$PWD/build/liblc_b200_x16.so timeout 600 python -m pytest tests/test_gpu_tensor.py tests/test_gpu_golden.py -x -q 2>&1 | tail -2 | tee -a gpurun_out/ab_x16.txt
