@@ -22,4 +22,11 @@ with lc.Context() as c:
     for k in range(5):
         c.l2_db_append(k, b)
     print(c.l2_loop_check(a, 10, 1)["n_good"])
+# the fused per-frame call (pair match vs the resident previous frame + append + loop check in one submission), both stores sizes
+with lc.Context(loop_threshold=0.15, min_loop_gap=3) as c:
+    tot = 0
+    for fid in range(14):
+        pair, cand, k = c.process_frame(fid, kfs[fid % 9])
+        tot += len(cand)
+    print("process_frame", tot)
 print("done")
