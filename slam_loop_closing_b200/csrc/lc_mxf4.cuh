@@ -232,6 +232,42 @@ __device__ __forceinline__ void release_stage(uint32_t acc_empty) {
   if ((threadIdx.x & 31) == 0) mbar_arrive_a(acc_empty);
 }
 
+#if LC_FX_DRAIN_EXPERIMENT == 4
+// timing experiment only: the same cells through the 16x256b access shape (16 lanes x 8 columns per request)
+template <int N>
+__device__ __forceinline__ void tmem_ld_16x256(uint32_t taddr, int (&v)[4 * N]);
+template <>
+__device__ __forceinline__ void tmem_ld_16x256<8>(uint32_t taddr, int (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.16x256b.x8.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+}
+template <>
+__device__ __forceinline__ void tmem_ld_16x256<4>(uint32_t taddr, int (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.16x256b.x4.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr)
+      : "memory");
+}
+template <>
+__device__ __forceinline__ void tmem_ld_16x256<2>(uint32_t taddr, int (&v)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.16x256b.x2.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+               : "r"(taddr)
+               : "memory");
+}
+#endif
+
 // Max over this thread's row of columns [taddr, taddr + ncols) of one accumulator stage (ncols: multiple of 16, <= 112),
 // then release the stage.  All loads of the half are issued at once (ptxas tracks each LDTM with its own scoreboard,
 // so the FMNMX3s of the first 32 columns run while the rest is still in flight) and the stage goes back to the MMA
@@ -239,6 +275,43 @@ __device__ __forceinline__ void release_stage(uint32_t acc_empty) {
 __device__ __forceinline__ float drain_accumulator(uint32_t taddr, int ncols, uint32_t acc_empty) {
   Max4 mx;
   mx.reset();
+#if LC_FX_DRAIN_EXPERIMENT == 6    // WRONG RESULTS, timing only: no TMEM load at all, 56 FMNMX3 on eight opaque values
+  if (ncols == kTN / 2) {
+    release_stage(acc_empty);
+    int s[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) asm volatile("mov.b32 %0, %1;" : "=r"(s[i]) : "r"(taddr + i));
+#pragma unroll
+    for (int r = 0; r < 2; ++r)
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = i + 1; j < 8; ++j) {  // 28 unordered pairs, twice (operands swapped): 56 distinct instructions
+          const float x = fmaxf(__int_as_float(r ? s[j] : s[i]), __int_as_float(r ? s[i] : s[j]) + (r ? 1.f : 0.f) * 0.f);
+          const int c = (i + j) & 3;
+          if (c == 0) mx.m0 = fmaxf(mx.m0, x);
+          if (c == 1) mx.m1 = fmaxf(mx.m1, x);
+          if (c == 2) mx.m2 = fmaxf(mx.m2, x);
+          if (c == 3) mx.m3 = fmaxf(mx.m3, x);
+        }
+  } else
+#endif
+#if LC_FX_DRAIN_EXPERIMENT == 4    // WRONG RESULTS, timing only: every cell loaded at once through the 16x256b shape, no fold
+  if (ncols == kTN / 2) {
+    int a0[32], a1[32], b0[16], b1[16], c0[8], c1[8];
+    const uint32_t hi = taddr + (16u << 16);
+    tmem_ld_16x256<8>(taddr, a0);
+    tmem_ld_16x256<8>(hi, a1);
+    tmem_ld_16x256<4>(taddr + 64, b0);
+    tmem_ld_16x256<4>(hi + 64, b1);
+    tmem_ld_16x256<2>(taddr + 96, c0);
+    tmem_ld_16x256<2>(hi + 96, c1);
+    tmem_ld_wait();
+    release_stage(acc_empty);
+    mx.m0 = fmaxf(__int_as_float(a0[0]), fmaxf(__int_as_float(a1[0]), __int_as_float(b0[0])));
+    mx.m1 = fmaxf(__int_as_float(b1[0]), fmaxf(__int_as_float(c0[0]), __int_as_float(c1[0])));
+  } else
+#endif
   if (ncols == kTN / 2) {  // the full tile: 112 = 32 + 32 + 32 + 16 columns
     int a[32], b[32], c[32], d[16];
     tmem_ld32(taddr, a);
@@ -691,7 +764,9 @@ __device__ __forceinline__ void resolve_best_body(int block, int n_blocks, const
         for (int u = kResolveGroups - 1; u >= 0; --u)
           if (hit[u]) found = j0 + 32 * u + __ffs(hit[u]) - 1;  // the lowest group wins
       }
+#if !LC_FX_DRAIN_EXPERIMENT
       if (found < 0) __trap();  // the distance came from this keyframe: a miss is a kernel bug
+#endif
       if (lane == 0) fr.best_packed[i] = ((uint64_t)d << 32) | (uint64_t)(kf.global_row_off + found);
     }
   }
