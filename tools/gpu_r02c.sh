@@ -1,7 +1,8 @@
 #!/bin/bash
-# round 2, session 2: timing-only builds (wrong results, -DLC_FX_DRAIN_EXPERIMENT=n) that take the drain's cost apart:
-# x1 = all TMEM loads at once, no fold; x2 = 64 of 112 columns loaded and folded; x3 = all loads, 64 columns folded;
-# x4 = x1 through the 16x256b access shape; x6 = no loads, 56 FMNMX3 on opaque values
+# round 2, session 2: the third / fourth TMEM load of a drain issued earlier (-DLC_FX_DRAIN_ORDER=1 [-DLC_FX_DRAIN_ORDER2=2|3])
 set -u
 mkdir -p gpurun_out
-bash tools/gpu_abn.sh ab_drain_cost2 50000 2 build/liblc_b200_x4.so build/liblc_b200_x6.so
+bash tools/gpu_abn.sh ab_drain_order 50000 3 build/liblc_b200_old.so build/liblc_b200_o1.so build/liblc_b200_o4.so build/liblc_b200_o5.so
+for L in build/liblc_b200_o5.so; do
+  LC_B200_LIB=$PWD/$L timeout 600 python -m pytest tests/test_gpu_tensor.py tests/test_gpu_golden.py -x -q 2>&1 | tail -2 | tee -a gpurun_out/ab_drain_order.txt
+done
