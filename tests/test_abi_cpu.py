@@ -147,3 +147,24 @@ def test_tmem_loads_are_waited_for():
     assert r.returncode == 0, r.stdout + r.stderr
     n_ldtm = int(re.search(r"(\d+) LDTM", r.stdout).group(1))
     assert n_ldtm >= 50, r.stdout  # the three tensor kernels were really looked at
+
+
+def test_cmake_build_exports_the_same_abi(tmp_path):
+    """The CMake build a C++ consumer (the reference is a CMake project) would use: configures, builds liblc_b200.so for
+    sm_100a and examples/abi_client against it; the library exports every declared entry point."""
+    import shutil
+    import subprocess
+    cmake = shutil.which("cmake")
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if cmake is None or not os.path.exists(nvcc):
+        pytest.skip("cmake / nvcc not available")
+    b = str(tmp_path / "build")
+    r = subprocess.run([cmake, "-S", ROOT, "-B", b, f"-DCMAKE_CUDA_COMPILER={nvcc}", "-DCMAKE_BUILD_TYPE=Release"],
+                       capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    r = subprocess.run([cmake, "--build", b, "-j", "4"], capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    lib = ctypes.CDLL(os.path.join(b, "liblc_b200.so"))
+    for n in declared_functions():
+        assert hasattr(lib, n), f"{n} missing from the CMake-built library"
+    assert os.path.exists(os.path.join(b, "abi_client"))
