@@ -922,7 +922,9 @@ struct NvtxRange {
   catch (const std::exception& e) { return fail((c), LC_ERR_INVALID, "%s", e.what()); }       \
   catch (...) { return fail((c), LC_ERR_INVALID, "unknown C++ exception"); }
 
-LC_API int32_t lc_abi_version(void) { return LC_ABI_VERSION; }
+// a timing-experiment build (-DLC_FX_DRAIN_EXPERIMENT=n, wrong results by design) answers with another version number, so it can
+// never pass for the library: tests/test_abi_cpu.py compares this value with the header's
+LC_API int32_t lc_abi_version(void) { return LC_ABI_VERSION + (LC_FX_DRAIN_EXPERIMENT ? 1000 : 0); }
 
 LC_API void lc_default_config(lc_config* g) {
   if (!g) return;
