@@ -426,7 +426,7 @@ def main():
                               "(profiles/), scaled to this launch's keyframes",
             "note": "per GPU; CUDA events on the library's stream around the matching kernel's launches inside the e2e timed "
                     "region; a fraction above 1 means the FP4 pipe holds its clock under the power cap better than cuBLAS bf16",
-            "what_is_left": "tensor pipe 93 % active, tensor-memory unit 94 % busy (ncu); the rest is the accumulator read-out - 4 B leave TMEM per 256 MACs because "
+            "what_is_left": "tensor pipe 93 % active (ncu); the rest is the accumulator read-out - 4 B leave TMEM per 256 MACs because "
                             "K = 256 is the descriptor length - beside the MMAs' own accumulator traffic, then 3 % tile padding "
                             "(2000 rows = 15.6 query tiles, 8.9 train tiles): profiles/r02_ab_drain_schedule.txt",
             "hbm": hbm, "int_popc": {"peak": popc_peak, "unit": "Gpairs/s", "x": pairs_s / 1e9 / popc_peak},
